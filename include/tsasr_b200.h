@@ -1,0 +1,126 @@
+/*
+ * tsasr_b200.h -- C ABI of the B200-native joint + RNN-T loss hot path (libtsasr_b200.so).
+ *
+ * The reference (lucadellalib/ts-asr) has no native boundary of its own: it is 100 % Python and
+ * reaches its kernels through torch.ops.torchaudio.rnnt_loss_forward and Numba @cuda.jit launches.
+ * Each entry point below cites the reference interface it replaces (paths relative to the
+ * reference root; SB = vendor/speechbrain/speechbrain).  INTEGRATION.md shows the ctypes binding a
+ * SpeechBrain maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless noted; nothing is allocated inside the library:
+ *     the caller owns all buffers (torch tensors) and passes a workspace where one is needed;
+ *   - `stream` is a cudaStream_t (the caller's current stream); no call synchronises the host;
+ *   - every function returns 0 on success or a negative TSASR_E_* code; tsasr_last_error() gives
+ *     the message (thread-local); nothing throws;
+ *   - B utterances, T = max frames, U = lattice width = max labels + 1, V = vocabulary incl. blank,
+ *     H = joint dimension;  logit_lengths[b] = T_b (1..T), target_lengths[b] = label count (0..U-1);
+ *     targets is int32 [B, U-1];
+ *   - lattice-sized arrays (lat2, den/logz, alpha, beta) hold tsasr_lattice_elems(B,T,U) elements in
+ *     the skewed layout: cell (b,t,u) at ((b*(T+U-1) + t+u) * U + u).
+ */
+#ifndef TSASR_B200_H
+#define TSASR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSASR_ABI_VERSION 1
+
+enum {
+    TSASR_OK = 0,
+    TSASR_E_INVALID = -1,     /* bad argument (shape, dtype, blank, alignment) */
+    TSASR_E_UNSUPPORTED = -2, /* shape outside what the sm_100a kernels implement */
+    TSASR_E_CUDA = -3,        /* CUDA runtime / driver error, see tsasr_last_error() */
+    TSASR_E_WORKSPACE = -4    /* workspace too small */
+};
+
+/* logits dtype codes */
+enum { TSASR_F32 = 0, TSASR_F16 = 1, TSASR_BF16 = 2 };
+
+/* activation codes: Transducer_joint(nonlinearity=...)  (SB/nnet/transducer/transducer_joint.py:40-46) */
+enum { TSASR_ACT_LEAKY_RELU = 0, TSASR_ACT_RELU = 1, TSASR_ACT_TANH = 2, TSASR_ACT_IDENTITY = 3 };
+
+typedef void* tsasr_stream_t; /* cudaStream_t */
+
+int tsasr_abi_version(void);
+const char* tsasr_last_error(void);
+
+/* Number of elements of one lattice-sized array: B * (T+U-1) * U. */
+size_t tsasr_lattice_elems(int B, int T, int U);
+
+/* ---- compat path: materialised logits in, dense dlogits out ------------------------------------
+ * Replaces torchaudio.functional.rnnt_loss as called at SB/nnet/losses.py:72-79
+ * (torch.ops.torchaudio.rnnt_loss_forward: ReduceMax2D / ReduceLogSumExpGivenMax2D / ComputeLogProbs),
+ * and `logits.log_softmax(-1)` + the label/blank gathers of the Numba kernels
+ * (SB/nnet/losses.py:84, SB/nnet/loss/transducer_loss.py:81-90,160-166).
+ * normalized != 0: rows are already log-probs (Transducer.apply input), den is set to 0.
+ * lat2: float2 {lp_blank, lp_emit} per cell; den: log-sum-exp per cell. */
+int tsasr_logits_to_lattice(const void* logits, int logits_dtype, const int32_t* targets,
+                            const int32_t* logit_lengths, const int32_t* target_lengths, int B, int T, int U, int V,
+                            int blank, int normalized, float* lat2, float* den, tsasr_stream_t stream);
+
+/* Anti-diagonal wavefront forward/backward DP.  Replaces cu_kernel_forward / cu_kernel_backward
+ * (SB/nnet/loss/transducer_loss.py:31-106,109-180) and torchaudio's ComputeAlphasBetasCosts.
+ * Outputs alpha, beta (lattice-sized), cost[b] = -log P(y_b|x_b) (from beta(0,0)), and the two
+ * log-likelihoods ll_alpha[b], ll_beta[b] (each B floats) for consistency checks. */
+int tsasr_lattice_alpha_beta(const float* lat2, const int32_t* logit_lengths, const int32_t* target_lengths, int B,
+                             int T, int U, float* alpha, float* beta, float* cost, float* ll_alpha, float* ll_beta,
+                             tsasr_stream_t stream);
+
+/* Dense gradient d cost_b / d logits * dcost[b] with the softmax folded in (torchaudio
+ * ComputeGradients; SB/nnet/losses.py:72-79 backward).  dcost may be NULL (= 1).  clamp <= 0: off.
+ * dlogits has the dtype and shape of logits; cells outside T_b x U_b are written as zeros. */
+int tsasr_logits_grad(const void* logits, int logits_dtype, const int32_t* targets, const int32_t* logit_lengths,
+                      const int32_t* target_lengths, int B, int T, int U, int V, int blank, const float* lat2,
+                      const float* den, const float* alpha, const float* beta, const float* cost, const float* dcost,
+                      float clamp, void* dlogits, tsasr_stream_t stream);
+
+/* Sparse gradient w.r.t. log-probs, fp32 [B,T,U,V] (zero-filled here), Numba semantics:
+ * cu_kernel_compute_grad, SB/nnet/loss/transducer_loss.py:183-236. */
+int tsasr_logprobs_grad(const int32_t* targets, const int32_t* logit_lengths, const int32_t* target_lengths, int B,
+                        int T, int U, int V, int blank, const float* lat2, const float* alpha, const float* beta,
+                        const float* cost, const float* dcost, float* grads, tsasr_stream_t stream);
+
+/* ---- fused path: joint + head + log-softmax, 4-D tensors never materialised ---------------------
+ * Replaces Transducer_joint.forward (joint="sum": SB/nnet/transducer/transducer_joint.py:73-74,95),
+ * Linear.forward of the transducer head (SB/nnet/linear.py:74) and the log-softmax + gathers of the
+ * loss, as chained at train_librispeechmix_scratch.py:132,135,158.
+ *   enc  bf16 [B,T,H]   dec bf16 [B,U,H]   W bf16 [V,H]   bias fp32 [V]
+ *   out: lat2 (float2 per cell), logz (log-sum-exp per cell), skewed layout.
+ * Requirements: H % 64 == 0, 64 <= H <= 640, V >= 2.  tcgen05 / TMEM / TMA kernel. */
+int tsasr_joint_fwd(const void* enc, const void* dec, const void* W, const float* bias, const int32_t* targets,
+                    const int32_t* logit_lengths, const int32_t* target_lengths, int B, int T, int U, int H, int V,
+                    int blank, int act_kind, float act_param, float* lat2, float* logz, tsasr_stream_t stream);
+
+/* Workspace (bytes) tsasr_joint_bwd needs; bounded independently of B*T*U by `max_chunk_cells`
+ * (0 = library default). */
+size_t tsasr_joint_bwd_workspace_bytes(int B, int T, int U, int H, int V, long long max_chunk_cells);
+
+/* Backward of the fused chain (autograd of Linear + activation + broadcast add fed by the loss
+ * gradient; reference: SB/core.py:1077 loss.backward()).  Recomputes the logits tile-wise, forms
+ * dlogits in bf16 chunk by chunk (never the whole [B,T,U,V]) and runs the two backward GEMMs.
+ *   out: d_enc fp32 [B,T,H], d_dec fp32 [B,U,H], dW fp32 [V,H], db fp32 [V]  (all overwritten). */
+int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float* bias, const int32_t* targets,
+                    const int32_t* logit_lengths, const int32_t* target_lengths, int B, int T, int U, int H, int V,
+                    int blank, int act_kind, float act_param, const float* lat2, const float* logz,
+                    const float* alpha, const float* beta, const float* cost, const float* dcost, void* workspace,
+                    size_t workspace_bytes, long long max_chunk_cells, float* d_enc, float* d_dec, float* dW,
+                    float* db, tsasr_stream_t stream);
+
+/* Test-only: dump the logits tile-wise recomputed by the tcgen05 mainloop into a dense fp32
+ * [B,T,U,V] buffer (small shapes), so the GEMM can be checked in isolation. */
+int tsasr_joint_debug_logits(const void* enc, const void* dec, const void* W, const float* bias, int B, int T, int U,
+                             int H, int V, int act_kind, float act_param, float* logits_out, tsasr_stream_t stream);
+
+/* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
+long long tsasr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSASR_B200_H */

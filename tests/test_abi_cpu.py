@@ -1,0 +1,98 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/tsasr_b200.h declares (no compute calls without a GPU), and the host logic that needs no
+kernels (length conversion, handle mechanics, error behaviour)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import tsasr_b200
+from tsasr_b200 import _build, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "tsasr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tsasr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    _build.build()
+    lib = ctypes.CDLL(_build.SO_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 10
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/tsasr_b200.h but not exported"
+    assert set(declared) == set(_lib.SIGNATURES), "ctypes binding and header disagree"
+    assert _lib.load().tsasr_abi_version() == 1
+    assert _lib.load().tsasr_lattice_elems(2, 5, 3) == 2 * 7 * 3
+
+
+def test_no_cpu_path():
+    logits = torch.randn(1, 3, 2, 5)
+    with pytest.raises(ValueError, match="CUDA"):
+        tsasr_b200.rnnt_loss(logits, torch.ones(1, 1, dtype=torch.int32), torch.tensor([3], dtype=torch.int32),
+                             torch.tensor([1], dtype=torch.int32), blank=0, check_lengths=False)
+    with pytest.raises(ValueError, match="cuda"):  # transducer_loss.py:348-351
+        tsasr_b200.TransducerLoss()(logits, torch.ones(1, 1, dtype=torch.int32), torch.tensor([3], dtype=torch.int32),
+                                    torch.tensor([1], dtype=torch.int32))
+
+
+def test_error_conventions_match_torchaudio():
+    from torchaudio.functional import rnnt_loss as ta
+
+    logits = torch.randn(1, 3, 2, 5)
+    good = dict(targets=torch.ones(1, 1, dtype=torch.int32), logit_lengths=torch.tensor([3], dtype=torch.int32),
+                target_lengths=torch.tensor([1], dtype=torch.int32))
+    for bad in (dict(good, targets=good["targets"].long()), dict(good, logit_lengths=good["logit_lengths"].long()),
+                dict(good, target_lengths=good["target_lengths"].long())):
+        with pytest.raises(RuntimeError):
+            ta(logits, **bad)
+        with pytest.raises(RuntimeError):
+            tsasr_b200.rnnt_loss(logits, **bad)
+    for fn in (ta, tsasr_b200.rnnt_loss):
+        with pytest.raises(ValueError):
+            fn(logits, reduction="batchmean", **good)
+        with pytest.raises(RuntimeError):
+            fn(logits, blank=7, **good)
+
+
+def test_transducer_joint_module_surface():
+    j = tsasr_b200.Transducer_joint()
+    assert isinstance(j.nonlinearity, torch.nn.LeakyReLU)
+    assert list(j.state_dict().keys()) == [] and list(j.buffers()) == []  # strict checkpoint loading
+    # CPU / decode-shaped inputs use the reference's eager math
+    tn, pn = torch.rand(8, 200, 1, 40), torch.rand(8, 1, 12, 40)
+    out = j(tn, pn)
+    assert torch.equal(out, torch.nn.functional.leaky_relu(tn + pn))
+    lin = torch.nn.Linear(80, 80)
+    jc = tsasr_b200.Transducer_joint(lin, joint="concat")
+    assert jc(tn, pn).shape == torch.Size([8, 200, 12, 80])  # the reference's doctest (transducer_joint.py:27-38)
+    with pytest.raises(ValueError):
+        j(torch.rand(3, 4), torch.rand(3))
+
+
+def test_joint_handle_defers_through_stock_linear_and_materialises_on_foreign_ops():
+    enc, dec = torch.randn(2, 6, 1, 64), torch.randn(2, 1, 5, 64)
+    act = torch.nn.LeakyReLU()
+    h = tsasr_b200.JointHandle(enc, dec, act, 0, 0.01)
+    assert h.shape == (2, 6, 5, 64) and h.ndim == 4 and h.dim() == 4 and h.device == enc.device
+    head = torch.nn.Linear(64, 11)
+    out = head(h)  # nn.Linear.forward -> F.linear(handle, W, b), exactly what SB/nnet/linear.py:74 issues
+    assert isinstance(out, tsasr_b200.JointHandle) and out.has_head and out.shape == (2, 6, 5, 11)
+    assert out._weight is head.weight and out._bias is head.bias
+    ref = head(act(enc + dec))
+    assert torch.allclose(out.materialize(), ref)
+    foreign = out * 1.0
+    assert type(foreign) is torch.Tensor and torch.allclose(foreign, ref)
+    assert torch.allclose(out.log_softmax(-1), ref.log_softmax(-1))
+
+
+def test_relative_length_conversion_bit_exact(golden):
+    g = golden("half_rounding_torchaudio")
+    rel = torch.tensor(g["input_rel"])
+    assert torch.equal((rel * 8).round().int(), torch.tensor(g["input_abs"]))

@@ -1,0 +1,428 @@
+// lattice.cu -- RNN-T lattice kernels (HBM/latency-bound part of the hot path).
+//
+//   logits_to_lattice_kernel : [B,T,U,V] logits -> 2-value lattice {lp_blank, lp_emit} + log-sum-exp
+//                              (replaces torchaudio's ReduceMax2D / ReduceLogSumExpGivenMax2D /
+//                               ComputeLogProbs and SB/nnet/losses.py:84 log_softmax on the compat path)
+//   alpha_beta_kernel        : anti-diagonal wavefront forward/backward DP
+//                              (replaces SB/nnet/loss/transducer_loss.py:31-180 cu_kernel_forward /
+//                               cu_kernel_backward and torchaudio's ComputeAlphasBetasCosts)
+//   logits_grad_kernel       : dense d cost / d logits with the softmax folded in (torchaudio
+//                              ComputeGradients semantics)
+//   logprobs_grad_kernel     : sparse gradient w.r.t. log-probs (SB/nnet/loss/transducer_loss.py:183-236)
+//
+// All lattice-sized arrays use the skewed layout of common.cuh (diagonal-major, u contiguous).
+#include "common.cuh"
+
+#include <cuda_fp16.h>
+
+namespace tsasr {
+
+static constexpr float kLog2e = 1.4426950408889634f;
+static constexpr float kLn2 = 0.6931471805599453f;
+
+template <typename T>
+__device__ __forceinline__ float to_float(T v);
+template <>
+__device__ __forceinline__ float to_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_float<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_float(float v);
+template <>
+__device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_f4(float4* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+// online (max, sum) update with a block of values already in registers
+__device__ __forceinline__ void online_update(float& m, float& s, const float* x, int n) {
+    float cm = x[0];
+#pragma unroll
+    for (int i = 1; i < 32; ++i)
+        if (i < n) cm = fmaxf(cm, x[i]);
+    const float mn = fmaxf(m, cm);
+    if (mn == -INFINITY) return;  // nothing but -inf so far
+    const float ms = mn * kLog2e;
+    float acc = s * exp2f(m * kLog2e - ms);
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+        if (i < n) acc += exp2f(fmaf(x[i], kLog2e, -ms));
+    s = acc;
+    m = mn;
+}
+
+__device__ __forceinline__ void warp_combine(float& m, float& s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+        const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        const float mn = fmaxf(m, m2);
+        if (mn == -INFINITY) { s = 0.f; m = mn; continue; }
+        s = s * exp2f((m - mn) * kLog2e) + s2 * exp2f((m2 - mn) * kLog2e);
+        m = mn;
+    }
+}
+
+// One warp per lattice cell (row of V logits).  Rows outside the utterance's T_b x U_b rectangle are
+// skipped entirely (no HBM traffic).  normalized != 0: input rows are already log-probs (den := 0).
+template <typename T>
+__global__ void __launch_bounds__(256)
+logits_to_lattice_kernel(const T* __restrict__ logits, const int* __restrict__ targets,
+                         const int* __restrict__ logit_lengths, const int* __restrict__ target_lengths,
+                         int B, int Tmax, int U, int V, int blank, int normalized,
+                         float2* __restrict__ lat2, float* __restrict__ den) {
+    const int warps_per_block = blockDim.x >> 5;
+    const long long cell = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (cell >= (long long)B * Tmax * U) return;
+    const int u = (int)(cell % U);
+    const int t = (int)((cell / U) % Tmax);
+    const int b = (int)(cell / ((long long)U * Tmax));
+    const int Tb = logit_lengths[b], Ub = target_lengths[b] + 1;
+    if (t >= Tb || u >= Ub) return;
+    const T* row = logits + (size_t)cell * V;
+
+    float lse = 0.f;
+    if (!normalized) {
+        float m = -INFINITY, s = 0.f;
+        if (sizeof(T) == 4 && (V & 3) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0)) {
+            const float4* row4 = reinterpret_cast<const float4*>(row);
+            const int V4 = V >> 2;
+            for (int base = 0; base < V4; base += 32 * 8) {
+                float x[32];
+                int n = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int idx = base + j * 32 + lane;
+                    if (idx < V4) {
+                        const float4 v = ldg_stream_f4(row4 + idx);
+                        x[4 * j + 0] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+                        n = 4 * j + 4;
+                    } else {
+                        x[4 * j + 0] = x[4 * j + 1] = x[4 * j + 2] = x[4 * j + 3] = -INFINITY;
+                    }
+                }
+                if (n > 0) online_update(m, s, x, 32);
+            }
+        } else {
+            for (int base = 0; base < V; base += 32 * 32) {
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int idx = base + j * 32 + lane;
+                    x[j] = idx < V ? to_float<T>(row[idx]) : -INFINITY;
+                }
+                online_update(m, s, x, 32);
+            }
+        }
+        warp_combine(m, s);
+        lse = m + __logf(s);
+    }
+    if (lane == 0) {
+        const float xb = to_float<T>(row[blank]);
+        float xe = -INFINITY;
+        if (u < Ub - 1) xe = to_float<T>(row[targets[(size_t)b * (U - 1) + u]]) - lse;
+        const size_t o = skew_index(b, t, u, Tmax, U);
+        lat2[o] = make_float2(xb - lse, xe);
+        den[o] = lse;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wavefront DP.  grid = (B, 2): blockIdx.y = 0 -> alpha, 1 -> beta.  Thread j owns one lattice
+// column (alpha: u = j, beta: u = U_b-1-j) and walks it in time; step s touches the anti-diagonal
+// d = s (alpha) or d = T_b+U_b-2-s (beta), which is one contiguous row of the skewed layout.  The
+// neighbour value moves by warp shuffle; between warps through a double-buffered shared slot and
+// one named barrier per step.  Lattice rows are prefetched PF diagonals ahead (they do not depend
+// on the DP state), so the per-step critical path is shuffle + logaddexp only.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kDpPrefetch = 4;
+
+template <bool BETA>
+__device__ __forceinline__ void dp_pass(const float2* __restrict__ lat, float* __restrict__ out, int Tb, int Ub,
+                                        int U, float* __restrict__ result, float* xchg /* [2][32] */) {
+    const int j = threadIdx.x;
+    const int lane = j & 31, warp = j >> 5;
+    const int nwarps = (Ub + 31) >> 5;
+    if (warp >= nwarps) return;
+    const int nthreads_active = nwarps << 5;
+    const int u = BETA ? (Ub - 1 - j) : j;  // may be negative for idle lanes of the last warp
+    const bool col_ok = j < Ub;
+    const int S = Tb + Ub - 1;
+
+    auto row_of = [&](int s) { return BETA ? (S - 1 - s) : s; };
+    auto fetch = [&](int s) -> float2 {
+        const int tl = s - j;
+        if (col_ok && tl >= 0 && tl < Tb) return lat[(size_t)row_of(s) * U + u];
+        return make_float2(0.f, 0.f);
+    };
+
+    float2 buf[kDpPrefetch];
+#pragma unroll
+    for (int k = 0; k < kDpPrefetch; ++k) buf[k] = fetch(k);
+
+    float carry = -INFINITY;  // alpha: a(t-1,u)+blank(t-1,u)   beta: b(t+1,u)
+    float pass = -INFINITY;   // alpha: a(t,u)+emit(t,u)        beta: b(t,u)      (handed to thread j+1)
+
+    for (int s0 = 0; s0 < S; s0 += kDpPrefetch) {
+#pragma unroll
+        for (int k = 0; k < kDpPrefetch; ++k) {
+            const int s = s0 + k;
+            if (s < S) {  // block-uniform
+                const float2 cell = buf[k];
+                buf[k] = fetch(s + kDpPrefetch);
+                float from_left = __shfl_up_sync(0xffffffffu, pass, 1);
+                if (lane == 0) from_left = warp == 0 ? -INFINITY : xchg[((s + 1) & 1) * 32 + warp - 1];
+                const int tl = s - j;
+                if (col_ok && tl >= 0 && tl < Tb) {
+                    float val;
+                    if (BETA) {
+                        if (tl == 0 && j == 0) val = cell.x;  // b(T-1,U-1) = lp_blank
+                        else {
+                            const float stay = carry + cell.x;
+                            const float emit = j == 0 ? -INFINITY : from_left + cell.y;
+                            val = logaddexp_fast(stay, emit);
+                        }
+                        carry = val;
+                        pass = val;
+                    } else {
+                        if (tl == 0 && j == 0) val = 0.f;  // a(0,0) = 0
+                        else val = logaddexp_fast(carry, j == 0 ? -INFINITY : from_left);
+                        carry = val + cell.x;
+                        pass = val + cell.y;
+                    }
+                    out[(size_t)row_of(s) * U + u] = val;
+                    if (tl == Tb - 1 && j == Ub - 1) *result = BETA ? val : carry;  // log P(y|x)
+                }
+                if (nwarps > 1) {
+                    if (lane == 31) xchg[(s & 1) * 32 + warp] = pass;
+                    asm volatile("bar.sync 1, %0;" ::"r"(nthreads_active) : "memory");
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+alpha_beta_kernel(const float2* __restrict__ lat2, const int* __restrict__ logit_lengths,
+                  const int* __restrict__ target_lengths, int Tmax, int U, float* __restrict__ alpha,
+                  float* __restrict__ beta, float* __restrict__ ll_alpha, float* __restrict__ ll_beta) {
+    __shared__ float xchg[64];
+    const int b = blockIdx.x;
+    const int Tb = logit_lengths[b], Ub = target_lengths[b] + 1;
+    const size_t base = (size_t)b * (size_t)(Tmax + U - 1) * (size_t)U;
+    // Each utterance's own rectangle starts at diagonal 0 of its slab: cell (t,u) -> row t+u.
+    if (blockIdx.y == 0) dp_pass<false>(lat2 + base, alpha + base, Tb, Ub, U, ll_alpha + b, xchg);
+    else dp_pass<true>(lat2 + base, beta + base, Tb, Ub, U, ll_beta + b, xchg);
+}
+
+// cost[b] = -log P from the beta pass (torchaudio: costs = -beta(0,0)); written by a tiny kernel so the
+// DP kernel keeps both log-likelihoods available for the consistency check in tests.
+__global__ void finalize_cost_kernel(const float* __restrict__ ll_beta, float* __restrict__ cost, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) cost[b] = -ll_beta[b];
+}
+
+// Per-cell occupation terms shared by every gradient kernel:
+//   occ = dy * exp(a + b - L)                      (= ob + oe)
+//   ob  = dy * exp(a + lp_blank + b(t+1,u) - L)    (terminal blank: b := 0)
+//   oe  = dy * exp(a + lp_emit  + b(t,u+1) - L)    (u < U_b-1)
+struct CellTerms { float occ, ob, oe; };
+__device__ __forceinline__ CellTerms cell_terms(const float2* __restrict__ lat2, const float* __restrict__ alpha,
+                                                const float* __restrict__ beta, float L, float dy, int b, int t, int u,
+                                                int Tb, int Ub, int Tmax, int U) {
+    const size_t o = skew_index(b, t, u, Tmax, U);
+    const float a = alpha[o];
+    const float2 lp = lat2[o];
+    CellTerms r;
+    r.occ = dy * __expf(a + beta[o] - L);
+    float bt1 = -INFINITY;
+    if (t < Tb - 1) bt1 = beta[o + U];  // (t+1,u): next diagonal, same u
+    else if (u == Ub - 1) bt1 = 0.f;
+    r.ob = bt1 == -INFINITY ? 0.f : dy * __expf(a + lp.x + bt1 - L);
+    r.oe = u < Ub - 1 ? dy * __expf(a + lp.y + beta[o + U + 1] - L) : 0.f;  // (t,u+1): next diagonal, u+1
+    return r;
+}
+
+// Dense d cost/d logits, one warp per cell; cells outside the rectangle get exact zeros.
+template <typename T>
+__global__ void __launch_bounds__(256)
+logits_grad_kernel(const T* __restrict__ logits, const int* __restrict__ targets,
+                   const int* __restrict__ logit_lengths, const int* __restrict__ target_lengths, int B, int Tmax,
+                   int U, int V, int blank, const float2* __restrict__ lat2, const float* __restrict__ den,
+                   const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ cost,
+                   const float* __restrict__ dcost, float clamp, T* __restrict__ dlogits) {
+    const int warps_per_block = blockDim.x >> 5;
+    const long long cell = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (cell >= (long long)B * Tmax * U) return;
+    const int u = (int)(cell % U);
+    const int t = (int)((cell / U) % Tmax);
+    const int b = (int)(cell / ((long long)U * Tmax));
+    const int Tb = logit_lengths[b], Ub = target_lengths[b] + 1;
+    const T* row = logits + (size_t)cell * V;
+    T* out = dlogits + (size_t)cell * V;
+    const bool vec = sizeof(T) == 4 && (V & 3) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (t >= Tb || u >= Ub) {
+        if (vec) {
+            float4* o4 = reinterpret_cast<float4*>(out);
+            for (int i = lane; i < (V >> 2); i += 32) stg_stream_f4(o4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        } else {
+            for (int i = lane; i < V; i += 32) out[i] = from_float<T>(0.f);
+        }
+        return;
+    }
+    const float dy = dcost ? dcost[b] : 1.f;
+    const CellTerms ct = cell_terms(lat2, alpha, beta, -cost[b], dy, b, t, u, Tb, Ub, Tmax, U);
+    const float nd = -den[skew_index(b, t, u, Tmax, U)] * kLog2e;
+    const int label = u < Ub - 1 ? targets[(size_t)b * (U - 1) + u] : -1;
+    auto grad = [&](float x, int v) {
+        float g = exp2f(fmaf(x, kLog2e, nd)) * ct.occ;
+        if (v == blank) g -= ct.ob;
+        if (v == label) g -= ct.oe;
+        if (clamp > 0.f) g = fminf(fmaxf(g, -clamp), clamp);
+        return g;
+    };
+    if (vec) {
+        const float4* r4 = reinterpret_cast<const float4*>(row);
+        float4* o4 = reinterpret_cast<float4*>(out);
+        const int V4 = V >> 2;
+        for (int base = 0; base < V4; base += 32 * 4) {
+            float4 x[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = base + j * 32 + lane;
+                if (idx < V4) x[j] = ldg_stream_f4(r4 + idx);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = base + j * 32 + lane;
+                if (idx < V4) {
+                    float4 g;
+                    g.x = grad(x[j].x, 4 * idx + 0);
+                    g.y = grad(x[j].y, 4 * idx + 1);
+                    g.z = grad(x[j].z, 4 * idx + 2);
+                    g.w = grad(x[j].w, 4 * idx + 3);
+                    stg_stream_f4(o4 + idx, g);
+                }
+            }
+        }
+    } else {
+        for (int i = lane; i < V; i += 32) out[i] = from_float<T>(grad(to_float<T>(row[i]), i));
+    }
+}
+
+// Sparse gradient w.r.t. log-probs (Numba semantics): -ob at blank, -oe at labels[b,u]; the dense
+// zero fill is a cudaMemsetAsync issued by the caller.  One thread per cell.
+__global__ void __launch_bounds__(256)
+logprobs_grad_kernel(const int* __restrict__ targets, const int* __restrict__ logit_lengths,
+                     const int* __restrict__ target_lengths, int B, int Tmax, int U, int V, int blank,
+                     const float2* __restrict__ lat2, const float* __restrict__ alpha,
+                     const float* __restrict__ beta, const float* __restrict__ cost,
+                     const float* __restrict__ dcost, float* __restrict__ grads) {
+    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= (long long)B * Tmax * U) return;
+    const int u = (int)(cell % U);
+    const int t = (int)((cell / U) % Tmax);
+    const int b = (int)(cell / ((long long)U * Tmax));
+    const int Tb = logit_lengths[b], Ub = target_lengths[b] + 1;
+    if (t >= Tb || u >= Ub) return;
+    const float dy = dcost ? dcost[b] : 1.f;
+    const CellTerms ct = cell_terms(lat2, alpha, beta, -cost[b], dy, b, t, u, Tb, Ub, Tmax, U);
+    float* g = grads + (size_t)cell * V;
+    if (t < Tb - 1 || u == Ub - 1) g[blank] = -ct.ob;
+    if (u < Ub - 1) g[targets[(size_t)b * (U - 1) + u]] = -ct.oe;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers (called from capi.cu)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t launch_logits_to_lattice_t(const void* logits, const int* targets, const int* ll, const int* tl,
+                                              int B, int Tmax, int U, int V, int blank, int normalized, float2* lat2,
+                                              float* den, cudaStream_t st) {
+    const long long cells = (long long)B * Tmax * U;
+    const int wpb = 8;
+    const long long blocks = (cells + wpb - 1) / wpb;
+    logits_to_lattice_kernel<T><<<(unsigned)blocks, wpb * 32, 0, st>>>(static_cast<const T*>(logits), targets, ll, tl,
+                                                                        B, Tmax, U, V, blank, normalized, lat2, den);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_logits_to_lattice(const void* logits, int dtype, const int* targets, const int* ll, const int* tl,
+                                     int B, int Tmax, int U, int V, int blank, int normalized, float2* lat2, float* den,
+                                     cudaStream_t st) {
+    switch (dtype) {
+        case 0: return launch_logits_to_lattice_t<float>(logits, targets, ll, tl, B, Tmax, U, V, blank, normalized, lat2, den, st);
+        case 1: return launch_logits_to_lattice_t<__half>(logits, targets, ll, tl, B, Tmax, U, V, blank, normalized, lat2, den, st);
+        case 2: return launch_logits_to_lattice_t<__nv_bfloat16>(logits, targets, ll, tl, B, Tmax, U, V, blank, normalized, lat2, den, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_alpha_beta(const float2* lat2, const int* ll, const int* tl, int B, int Tmax, int U, float* alpha,
+                              float* beta, float* ll_alpha, float* ll_beta, float* cost, cudaStream_t st) {
+    const int threads = ((U + 31) / 32) * 32;
+    alpha_beta_kernel<<<dim3(B, 2), threads, 0, st>>>(lat2, ll, tl, Tmax, U, alpha, beta, ll_alpha, ll_beta);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    finalize_cost_kernel<<<(B + 127) / 128, 128, 0, st>>>(ll_beta, cost, B);
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_logits_grad_t(const void* logits, const int* targets, const int* ll, const int* tl, int B,
+                                        int Tmax, int U, int V, int blank, const float2* lat2, const float* den,
+                                        const float* alpha, const float* beta, const float* cost, const float* dcost,
+                                        float clamp, void* dlogits, cudaStream_t st) {
+    const long long cells = (long long)B * Tmax * U;
+    const int wpb = 8;
+    const long long blocks = (cells + wpb - 1) / wpb;
+    logits_grad_kernel<T><<<(unsigned)blocks, wpb * 32, 0, st>>>(static_cast<const T*>(logits), targets, ll, tl, B, Tmax,
+                                                                  U, V, blank, lat2, den, alpha, beta, cost, dcost,
+                                                                  clamp, static_cast<T*>(dlogits));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_logits_grad(const void* logits, int dtype, const int* targets, const int* ll, const int* tl, int B,
+                               int Tmax, int U, int V, int blank, const float2* lat2, const float* den,
+                               const float* alpha, const float* beta, const float* cost, const float* dcost,
+                               float clamp, void* dlogits, cudaStream_t st) {
+    switch (dtype) {
+        case 0: return launch_logits_grad_t<float>(logits, targets, ll, tl, B, Tmax, U, V, blank, lat2, den, alpha, beta, cost, dcost, clamp, dlogits, st);
+        case 1: return launch_logits_grad_t<__half>(logits, targets, ll, tl, B, Tmax, U, V, blank, lat2, den, alpha, beta, cost, dcost, clamp, dlogits, st);
+        case 2: return launch_logits_grad_t<__nv_bfloat16>(logits, targets, ll, tl, B, Tmax, U, V, blank, lat2, den, alpha, beta, cost, dcost, clamp, dlogits, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_logprobs_grad(const int* targets, const int* ll, const int* tl, int B, int Tmax, int U, int V,
+                                 int blank, const float2* lat2, const float* alpha, const float* beta,
+                                 const float* cost, const float* dcost, float* grads, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)B * Tmax * U * V, st);
+    if (e != cudaSuccess) return e;
+    const long long cells = (long long)B * Tmax * U;
+    logprobs_grad_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(targets, ll, tl, B, Tmax, U, V, blank, lat2,
+                                                                          alpha, beta, cost, dcost, grads);
+    return cudaGetLastError();
+}
+
+}  // namespace tsasr

@@ -1,0 +1,195 @@
+"""Autograd functions and the functional API of the B200-native RNN-T loss.
+
+``rnnt_loss`` mirrors ``torchaudio.functional.rnnt_loss`` -- the op the reference reaches at
+vendor/speechbrain/speechbrain/nnet/losses.py:72-79 -- in signature, semantics and error behaviour
+(same exception types for the same precondition violations).
+"""
+import torch
+
+from . import _lib, ops
+
+
+def _check_reduction(reduction):
+    if reduction not in ("none", "mean", "sum"):
+        raise ValueError('reduction should be one of "none", "mean", or "sum"')
+
+
+def _reduce(costs, reduction):
+    # torchaudio/functional/functional.py:1791-1794: reduction is applied OUTSIDE the autograd
+    # Function, so "mean" back-propagates 1/B.
+    if reduction == "mean":
+        return costs.mean()
+    if reduction == "sum":
+        return costs.sum()
+    return costs
+
+
+def _validate_lengths(logit_lengths, target_lengths, T, U, n_targets):
+    """The checks torchaudio performs on the host (one small device->host read, as the reference does)."""
+    stats = torch.stack([logit_lengths.max(), target_lengths.max(), logit_lengths.min(), target_lengths.min()]).tolist()
+    max_t, max_l, min_t, min_l = (int(v) for v in stats)
+    if max_t != T:
+        raise RuntimeError("input length mismatch")
+    if max_l + 1 != U:
+        raise RuntimeError("output length mismatch")
+    if n_targets != max_l:
+        raise RuntimeError("target length mismatch")
+    if min_t < 1 or min_l < 0:
+        raise RuntimeError("logit_lengths must be >= 1 and target_lengths >= 0")
+
+
+class RnntLossFromLogits(torch.autograd.Function):
+    """costs[b] = -log P(y_b | x_b) from materialised logits; backward emits dense dlogits.
+
+    Compat path: three HBM-bound kernels (log-sum-exp + gather, wavefront DP, gradient); the logits
+    are read once in forward and once in backward, dlogits is written once.
+    """
+
+    @staticmethod
+    def forward(ctx, logits, targets, logit_lengths, target_lengths, blank, clamp):
+        B, T, U, V = logits.shape
+        lat2, den = ops.logits_to_lattice(logits, targets, logit_lengths, target_lengths, blank)
+        alpha, beta, cost, _, _ = ops.alpha_beta(lat2, logit_lengths, target_lengths, B, T, U)
+        ctx.save_for_backward(logits, targets, logit_lengths, target_lengths, lat2, den, alpha, beta, cost)
+        ctx.blank, ctx.clamp = blank, clamp
+        return cost.to(logits.dtype)
+
+    @staticmethod
+    def backward(ctx, dcost):
+        logits, targets, ll, tl, lat2, den, alpha, beta, cost = ctx.saved_tensors
+        dcost = dcost.to(torch.float32).contiguous()
+        dlogits = ops.logits_grad(logits, targets, ll, tl, ctx.blank, lat2, den, alpha, beta, cost, dcost, ctx.clamp)
+        return dlogits, None, None, None, None, None
+
+
+def rnnt_loss(logits, targets, logit_lengths, target_lengths, blank=-1, clamp=-1.0, reduction="mean",
+              fused_log_softmax=True, check_lengths=True):
+    """Drop-in for ``torchaudio.functional.rnnt_loss`` on CUDA tensors (absolute int32 lengths)."""
+    _check_reduction(reduction)
+    if logits.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        raise RuntimeError("logits must be float32, float16 or bfloat16")
+    if targets.dtype != torch.int32:
+        raise RuntimeError("targets must be int32 type")
+    if logit_lengths.dtype != torch.int32:
+        raise RuntimeError("logit_lengths must be int32 type")
+    if target_lengths.dtype != torch.int32:
+        raise RuntimeError("target_lengths must be int32 type")
+    if logits.dim() != 4:
+        raise RuntimeError("logits must be 4-D (batch, time, target, class)")
+    if targets.dim() != 2:
+        raise RuntimeError("targets must be 2-D (batch, max target length)")
+    if not logits.is_contiguous():
+        raise RuntimeError("logits must be contiguous")
+    B, T, U, V = logits.shape
+    if targets.shape[0] != B or logit_lengths.shape[0] != B or target_lengths.shape[0] != B:
+        raise RuntimeError("batch dimension mismatch between logits, targets and lengths")
+    if blank < 0:
+        blank += V  # torchaudio accepts negative indices (default -1)
+    if not 0 <= blank < V:
+        raise RuntimeError("blank must be within [0, logits.shape[-1])")
+    if check_lengths:
+        _validate_lengths(logit_lengths, target_lengths, T, U, targets.shape[1])
+    if not fused_log_softmax:
+        logits = torch.nn.functional.log_softmax(logits, dim=-1)
+    costs = RnntLossFromLogits.apply(logits, targets.contiguous(), logit_lengths.contiguous(),
+                                     target_lengths.contiguous(), int(blank), float(clamp))
+    return _reduce(costs, reduction)
+
+
+class NumbaSemanticsTransducer(torch.autograd.Function):
+    """``Transducer.apply(log_probs, labels, T, U, blank, reduction)`` --
+    vendor/speechbrain/speechbrain/nnet/loss/transducer_loss.py:239-293, quirks included:
+    value = reduce_b(-log P_b / T_b) with the reduction applied inside forward (:280-287), stored
+    gradient w.r.t. the log-probs is the un-normalised occupation (:183-236), backward multiplies it by
+    grad_output (:289-293)."""
+
+    @staticmethod
+    def forward(ctx, log_probs, labels, T, U, blank, reduction):
+        log_probs = log_probs.detach()
+        if log_probs.dtype != torch.float32:
+            raise TypeError("log_probs must be float32 (the reference kernels are typed float32[:,:,:,:])")
+        if labels.dtype != torch.int32 or T.dtype != torch.int32 or U.dtype != torch.int32:
+            raise TypeError("labels, T and U must be int32 (the reference kernels are typed int32)")
+        Bn, maxT, maxU, A = log_probs.shape
+        log_probs = log_probs.contiguous()
+        lat2, _ = ops.logits_to_lattice(log_probs, labels, T, U, blank, normalized=True)
+        alpha, beta, cost, _, _ = ops.alpha_beta(lat2, T, U, Bn, maxT, maxU)
+        ones = torch.ones((Bn,), dtype=torch.float32, device=log_probs.device)
+        ctx.grads = ops.logprobs_grad(tuple(log_probs.shape), labels, T, U, blank, lat2, alpha, beta, cost, ones)
+        per_utt = cost / T.to(torch.float32)  # transducer_loss.py:104-106
+        if reduction == "mean":
+            return per_utt.mean()
+        elif reduction == "sum":
+            return per_utt.sum()
+        elif reduction == "none":
+            return per_utt
+        else:
+            raise Exception("Unexpected reduction {}".format(reduction))
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        grad_output = grad_output.view(-1, 1, 1, 1).to(ctx.grads)
+        return ctx.grads.mul_(grad_output), None, None, None, None, None, None
+
+
+class FusedJointRnnt(torch.autograd.Function):
+    """costs[b] of joint("sum") + activation + head Linear + RNN-T loss without the 4-D tensors.
+
+    Differentiable inputs: enc_out [B,T,H], dec_out [B,U,H], W [V,H], bias [V]
+    (train_librispeechmix_scratch.py:122,127,135).  Operands are rounded to bf16 once on entry; all
+    accumulation is fp32 (TMEM), the lattice is fp32.
+    """
+
+    @staticmethod
+    def forward(ctx, enc, dec, W, bias, targets, logit_lengths, target_lengths, blank, act_kind, act_param,
+                max_chunk_cells):
+        enc16 = enc.detach().to(torch.bfloat16).contiguous()
+        dec16 = dec.detach().to(torch.bfloat16).contiguous()
+        W16 = W.detach().to(torch.bfloat16).contiguous()
+        b32 = bias.detach().to(torch.float32).contiguous()
+        B, T, _ = enc16.shape
+        U = dec16.shape[1]
+        lat2, logz = ops.joint_fwd(enc16, dec16, W16, b32, targets, logit_lengths, target_lengths, blank, act_kind, act_param)
+        alpha, beta, cost, _, _ = ops.alpha_beta(lat2, logit_lengths, target_lengths, B, T, U)
+        ctx.save_for_backward(enc16, dec16, W16, b32, targets, logit_lengths, target_lengths, lat2, logz, alpha, beta, cost)
+        ctx.cfg = (blank, act_kind, act_param, max_chunk_cells)
+        ctx.in_dtypes = (enc.dtype, dec.dtype, W.dtype, bias.dtype)
+        return cost
+
+    @staticmethod
+    def backward(ctx, dcost):
+        enc16, dec16, W16, b32, targets, ll, tl, lat2, logz, alpha, beta, cost = ctx.saved_tensors
+        blank, act_kind, act_param, max_chunk_cells = ctx.cfg
+        dcost = dcost.to(torch.float32).contiguous()
+        d_enc, d_dec, dW, db = ops.joint_bwd(enc16, dec16, W16, b32, targets, ll, tl, blank, act_kind, act_param,
+                                             lat2, logz, alpha, beta, cost, dcost, max_chunk_cells)
+        de, dd, dw, dbt = ctx.in_dtypes
+        return (d_enc.to(de), d_dec.to(dd), dW.to(dw), db.to(dbt), None, None, None, None, None, None, None)
+
+
+def fused_joint_rnnt_loss(enc_out, dec_out, weight, bias, targets, logit_lengths, target_lengths, blank=0,
+                          activation="leaky_relu", act_param=0.01, reduction="mean", check_lengths=True,
+                          max_chunk_cells=0):
+    """Functional form of the fused path (absolute int32 lengths)."""
+    _check_reduction(reduction)
+    if enc_out.dim() != 3 or dec_out.dim() != 3:
+        raise ValueError("enc_out must be [B,T,H] and dec_out [B,U,H]")
+    B, T, H = enc_out.shape
+    U = dec_out.shape[1]
+    V = weight.shape[0]
+    if dec_out.shape[0] != B or dec_out.shape[2] != H or weight.shape[1] != H:
+        raise ValueError("shape mismatch between enc_out, dec_out and weight")
+    if bias is None:
+        bias = torch.zeros((V,), dtype=torch.float32, device=enc_out.device)
+    if blank < 0:
+        blank += V
+    if not 0 <= blank < V:
+        raise RuntimeError("blank must be within [0, logits.shape[-1])")
+    targets = targets.to(torch.int32).contiguous()
+    logit_lengths = logit_lengths.to(torch.int32).contiguous()
+    target_lengths = target_lengths.to(torch.int32).contiguous()
+    if check_lengths:
+        _validate_lengths(logit_lengths, target_lengths, T, U, targets.shape[1])
+    costs = FusedJointRnnt.apply(enc_out, dec_out, weight, bias, targets, logit_lengths, target_lengths, int(blank),
+                                 _lib.ACT_CODES[activation], float(act_param), int(max_chunk_cells))
+    return _reduce(costs, reduction)
