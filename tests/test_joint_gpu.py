@@ -79,3 +79,135 @@ def test_fused_forward_lattice_vs_compat_path():
         torch.testing.assert_close(zf[bi, :Tb, :Ub], zc[bi, :Tb, :Ub], rtol=1e-5, atol=2e-5)
         torch.testing.assert_close(lf[bi, :Tb, :Ub, 0], lc[bi, :Tb, :Ub, 0], rtol=1e-5, atol=2e-5)
         torch.testing.assert_close(lf[bi, :Tb, :Ub - 1, 1], lc[bi, :Tb, :Ub - 1, 1], rtol=1e-5, atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# backward
+# ---------------------------------------------------------------------------------------------
+def _rel_err(got, ref):
+    return (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-12)
+
+
+GRAD_REL = 1e-2  # operand gradients: bf16 dlogits/J operands (2^-9 relative each), fp32 accumulation
+
+
+def _choose_tile_log2(T, U):
+    best, best_l = -1, 4
+    for l in range(3, 8):
+        tT, tU = 1 << l, 128 >> l
+        padded = ((T + tT - 1) // tT) * tT * ((U + tU - 1) // tU) * tU
+        if best < 0 or padded < best or (padded == best and l == 4):
+            best, best_l = padded, l
+    return best_l
+
+
+def _decode_dy_images(ws, B, T, U, V):
+    """Rebuild dense dlogits [B,T,U,V] from the bf16 SWIZZLE_128B operand images in the workspace
+    (single-chunk runs only) -- the test-only view of the never-materialised dlogits."""
+    l = _choose_tile_log2(T, U)
+    tT, tU = 1 << l, 128 >> l
+    nTt, nTu = (T + tT - 1) // tT, (U + tU - 1) // tU
+    NT4 = 4 * ((V + 255) // 256)
+    n_tiles = B * nTt * nTu
+    base = (-ws.data_ptr()) % 1024
+    raw = ws[base: base + n_tiles * NT4 * 16384].view(torch.bfloat16).view(n_tiles, NT4, 128, 64).float().cpu()
+    # un-swizzle: 16-byte chunk c of row r is stored at chunk c ^ (r & 7)
+    r = torch.arange(128)[:, None]
+    c = torch.arange(8)[None, :]
+    src_chunk = (c ^ (r & 7))  # [128, 8]
+    idx = (src_chunk[:, :, None] * 8 + torch.arange(8)[None, None, :]).reshape(128, 64)
+    img = torch.gather(raw, 3, idx[None, None].expand(n_tiles, NT4, 128, 64))
+    out = torch.zeros(B, T, U, V)
+    for tile in range(n_tiles):
+        b, rem = divmod(tile, nTt * nTu)
+        tt, tu = divmod(rem, nTu)
+        rows = img[tile].permute(1, 0, 2).reshape(128, NT4 * 64)[:, :V]  # [128 rows, V]
+        for row in range(128):
+            ti, ui = row % tT, row // tT
+            t, u = tt * tT + ti, tu * tU + ui
+            if t < T and u < U:
+                out[b, t, u] = rows[row]
+    return out
+
+
+@pytest.mark.parametrize("shape,act", [((2, 24, 9, 64, 40), "leaky_relu"), ((2, 16, 6, 64, 33), "tanh"),
+                                       ((2, 40, 17, 640, 1000), "leaky_relu"), ((2, 30, 40, 320, 29), "relu"),
+                                       ((3, 20, 1, 128, 50), "leaky_relu"), ((1, 9, 130, 384, 257), "leaky_relu")])
+def test_fused_backward_vs_reference_chain(shape, act):
+    B, T, U, H, V = shape
+    enc, dec, W, b, targets, ll, tl = _inputs(B, T, U, H, V, seed=sum(shape) + 2)
+    d = _dev()
+    dcost = torch.linspace(0.5, 1.5, B)
+    e, dc, w, bb = (x.to(d).float().requires_grad_() for x in (enc, dec, W, b))
+    costs = tsasr_b200.fused_joint_rnnt_loss(e, dc, w, bb, targets.to(d), ll.to(d), tl.to(d), blank=0, activation=act,
+                                             reduction="none", max_chunk_cells=1 << 30)
+    (costs * dcost.to(d)).sum().backward()
+    ref = reference_joint_loss_fwd_bwd(enc, dec, W, b, targets, ll, tl, 0, act, 0.01, round_bf16=True, dcost=dcost)
+    np.testing.assert_allclose(costs.detach().cpu().numpy(), ref["costs"].numpy(), rtol=LOSS_RTOL)
+    errs = {k: _rel_err(g.grad.cpu(), ref[k]) for k, g in (("d_enc", e), ("d_dec", dc), ("dW", w), ("db", bb))}
+    assert all(v < GRAD_REL for v in errs.values()), errs
+    # padding rows of d_enc / d_dec are exactly zero
+    for bi in range(B):
+        assert not e.grad[bi, int(ll[bi]):].any() and not dc.grad[bi, int(tl[bi]) + 1:].any()
+
+
+def test_fused_dlogits_images_vs_oracle():
+    """Test-only view of the tile-wise dlogits (bf16 operand images): 1e-3 max-abs (north_star) plus the
+    bf16 rounding of the value itself (2^-8 relative)."""
+    from oracle import rnnt_numpy as rn
+
+    B, T, U, H, V = 2, 20, 7, 64, 90
+    enc, dec, W, b, targets, ll, tl = _inputs(B, T, U, H, V, seed=5)
+    d = _dev()
+    e, dc, w, bb = (x.to(d).float().requires_grad_() for x in (enc, dec, W, b))
+    costs = tsasr_b200.fused_joint_rnnt_loss(e, dc, w, bb, targets.to(d), ll.to(d), tl.to(d), blank=0,
+                                             reduction="none", max_chunk_cells=1 << 30)
+    costs.sum().backward()
+    torch.cuda.synchronize()
+    got = _decode_dy_images(ops._workspaces[d], B, T, U, V).numpy()
+    _, logits = rn.joint_logits(enc.float().numpy(), dec.float().numpy(), W.float().numpy(), b.numpy(), "leaky_relu")
+    _, want = rn.rnnt_torchaudio(logits, targets.numpy(), ll.numpy(), tl.numpy(), 0)
+    assert np.all(np.abs(got - want) <= 1e-3 + np.abs(want) * 2.0 ** -8), np.abs(got - want).max()
+
+
+def test_fused_backward_chunked_equals_single_chunk():
+    B, T, U, H, V = 3, 48, 20, 128, 200
+    enc, dec, W, b, targets, ll, tl = _inputs(B, T, U, H, V, seed=21)
+    d = _dev()
+    grads = []
+    for chunk in (1 << 30, 128 * 7):
+        e, dc, w, bb = (x.to(d).float().requires_grad_() for x in (enc, dec, W, b))
+        loss = tsasr_b200.fused_joint_rnnt_loss(e, dc, w, bb, targets.to(d), ll.to(d), tl.to(d), blank=0,
+                                                reduction="mean", max_chunk_cells=chunk)
+        loss.backward()
+        grads.append([g.grad.clone() for g in (e, dc, w, bb)])
+    for a, c in zip(*grads):
+        assert _rel_err(c, a) < 1e-5  # same arithmetic, different fp32 summation grouping
+
+
+@pytest.mark.parametrize("name", ["joint_leaky", "joint_tanh", "joint_relu"])
+def test_drop_in_modules_vs_golden(golden, name):
+    """Transducer_joint -> stock Linear-style head -> transducer_loss, exactly the recipe's three
+    call sites (train_librispeechmix_scratch.py:132,135,158), against vectors produced by the reference."""
+    g = golden(name)
+    d = _dev()
+    act = {"leaky_relu": torch.nn.LeakyReLU, "tanh": torch.nn.Tanh, "relu": torch.nn.ReLU}[str(g["act"])]
+    enc = torch.tensor(g["enc"], device=d, requires_grad=True)
+    dec = torch.tensor(g["dec"], device=d, requires_grad=True)
+    V, H = g["W"].shape
+    head = torch.nn.Linear(H, V).to(d)
+    with torch.no_grad():
+        head.weight.copy_(torch.tensor(g["W"]))
+        head.bias.copy_(torch.tensor(g["b"]))
+    joiner = tsasr_b200.Transducer_joint(joint="sum", nonlinearity=act)
+    joint = joiner(enc[..., None, :], dec[:, None, ...])
+    assert isinstance(joint, tsasr_b200.JointHandle)
+    logits = head(joint)
+    assert isinstance(logits, tsasr_b200.JointHandle) and logits.shape == (*joint.shape[:3], V)
+    loss = tsasr_b200.transducer_loss(logits, torch.tensor(g["targets"], device=d).long(),
+                                      torch.tensor(g["input_rel"], device=d), torch.tensor(g["target_rel"], device=d),
+                                      blank_index=0, reduction=str(g["reduction"]), use_torchaudio=True)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=LOSS_RTOL)
+    for got, key in ((enc.grad, "d_enc"), (dec.grad, "d_dec"), (head.weight.grad, "dW"), (head.bias.grad, "db")):
+        assert _rel_err(got.cpu(), torch.tensor(g[key])) < GRAD_REL, key

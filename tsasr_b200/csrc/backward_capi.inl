@@ -1,8 +1,177 @@
+// backward_capi.inl -- tsasr_joint_bwd: chunked backward of the fused joint (included by capi.cu).
+//
+// Per chunk of cell tiles (sized to stay L2-resident, aligned to whole (utterance, frame-tile) groups):
+//   1. joint_gemm_kernel<MODE_GRAD>  recompute logits, emit bf16 dlogits + J operand images
+//   2. dj_gemm_kernel                dJ = dlogits * W, act', in-tile broadcast sums -> partial rows
+//   3. reduce_dpre_{enc,dec}_kernel  fold partial rows into d_enc / d_dec (deterministic)
+//   4. dw_gemm_kernel                dW/db split-K partials (+= across chunks, plain RMW, deterministic)
+// and a final reduce_dw_kernel over the split-K partials.
+
+namespace {
+
+struct BwdPlan {
+    int chunk_tiles;      // multiple of nTu
+    int n_chunks;
+    int n_splits;
+    int NVT, NHT, NVB, NT4;
+    size_t dY_bytes, J_bytes, part_bytes, dW_bytes, db_bytes, total;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static void plan_bwd(const JointParams& jp, int num_sms, long long max_chunk_cells, BwdPlan* pl) {
+    const int tT = 1 << jp.tT_log2, tU = 128 >> jp.tT_log2;
+    const int total_tiles = jp.B * jp.nTt * jp.nTu;
+    long long want_tiles = max_chunk_cells > 0 ? max_chunk_cells / 128 : (long long)num_sms;
+    if (want_tiles < 1) want_tiles = 1;
+    int groups = (int)((want_tiles + jp.nTu - 1) / jp.nTu);
+    if (groups < 1) groups = 1;
+    pl->chunk_tiles = groups * jp.nTu;
+    if (pl->chunk_tiles > total_tiles) pl->chunk_tiles = total_tiles;
+    pl->n_chunks = (total_tiles + pl->chunk_tiles - 1) / pl->chunk_tiles;
+    pl->NVB = (jp.V + 63) / 64;
+    pl->NT4 = jp.NT * 4;
+    pl->NVT = (jp.V + 127) / 128;
+    pl->NHT = (jp.KB + 3) / 4;
+    int splits = num_sms / (pl->NVT * pl->NHT);
+    if (splits < 1) splits = 1;
+    if (splits > pl->chunk_tiles) splits = pl->chunk_tiles;
+    pl->n_splits = splits;
+    pl->dY_bytes = align_up((size_t)pl->chunk_tiles * pl->NT4 * kImgBytes, 1024);
+    pl->J_bytes = align_up((size_t)pl->chunk_tiles * jp.KB * kImgBytes, 1024);
+    pl->part_bytes = align_up((size_t)pl->chunk_tiles * (tT + tU) * jp.H * 4, 1024);
+    pl->dW_bytes = align_up((size_t)pl->n_splits * pl->NVT * 128 * jp.H * 4, 1024);
+    pl->db_bytes = align_up((size_t)pl->n_splits * pl->NVT * 128 * 4, 1024);
+    pl->total = pl->dY_bytes + pl->J_bytes + pl->part_bytes + pl->dW_bytes + pl->db_bytes + 1024;
+}
+
+static int fake_params_for_plan(JointParams& p, int B, int T, int U, int H, int V) {
+    if (H % 64 != 0 || H < 64 || H > 64 * kMaxKB || V < 2 || B < 1 || T < 1 || U < 1) return -1;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.T = T; p.U = U; p.H = H; p.V = V;
+    choose_tile(T, U, &p.tT_log2);
+    const int tT = 1 << p.tT_log2, tU = 128 >> p.tT_log2;
+    p.nTt = (T + tT - 1) / tT;
+    p.nTu = (U + tU - 1) / tU;
+    p.KB = H / 64;
+    p.NT = (V + kTileN - 1) / kTileN;
+    return 0;
+}
+
+}  // namespace
+
 extern "C" {
-size_t tsasr_joint_bwd_workspace_bytes(int, int, int, int, int, long long) { return 0; }
-int tsasr_joint_bwd(const void*, const void*, const void*, const float*, const int32_t*, const int32_t*, const int32_t*,
-                    int, int, int, int, int, int, int, float, const float*, const float*, const float*, const float*,
-                    const float*, const float*, void*, size_t, long long, float*, float*, float*, float*, tsasr_stream_t) {
-    return fail(TSASR_E_UNSUPPORTED, "not built yet");
+
+size_t tsasr_joint_bwd_workspace_bytes(int B, int T, int U, int H, int V, long long max_chunk_cells) {
+    JointParams p;
+    if (fake_params_for_plan(p, B, T, U, H, V) != 0) return 0;
+    int sms = 148, max_smem = 0;
+    if (device_info(&sms, &max_smem) != TSASR_OK) sms = 148;  // sizing only; the launch re-checks the device
+    BwdPlan pl;
+    plan_bwd(p, sms, max_chunk_cells, &pl);
+    return pl.total;
 }
+
+int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float* bias, const int32_t* targets,
+                    const int32_t* logit_lengths, const int32_t* target_lengths, int B, int T, int U, int H, int V,
+                    int blank, int act_kind, float act_param, const float* lat2, const float* logz,
+                    const float* alpha, const float* beta, const float* cost, const float* dcost, void* workspace,
+                    size_t workspace_bytes, long long max_chunk_cells, float* d_enc, float* d_dec, float* dW,
+                    float* db, tsasr_stream_t stream) {
+    if (int rc = check_dims(B, T, U, V, blank)) return rc;
+    REQUIRE(enc && dec && W && bias && logit_lengths && target_lengths && lat2 && logz && alpha && beta && cost &&
+                workspace && d_enc && d_dec && dW && db, "null pointer argument");
+    REQUIRE(U == 1 || targets, "targets must not be null when U > 1");
+    int sms, max_smem;
+    if (int rc = device_info(&sms, &max_smem)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    JointParams jp;
+    if (int rc = fill_joint_params(jp, enc, dec, bias, targets, logit_lengths, target_lengths, B, T, U, H, V, blank,
+                                   act_kind, act_param, max_smem))
+        return rc;
+    BwdPlan pl;
+    plan_bwd(jp, sms, max_chunk_cells, &pl);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(workspace), 1024));
+    if ((size_t)(ws - static_cast<uint8_t*>(workspace)) + pl.total - 1024 > workspace_bytes)
+        return fail(TSASR_E_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total, workspace_bytes);
+
+    jp.lat2_in = reinterpret_cast<const float2*>(lat2);
+    jp.logz_in = logz;
+    jp.alpha = alpha;
+    jp.beta = beta;
+    jp.cost = cost;
+    jp.dcost = dcost;
+    jp.dY_img = reinterpret_cast<__nv_bfloat16*>(ws);
+    jp.J_img = reinterpret_cast<__nv_bfloat16*>(ws + pl.dY_bytes);
+
+    BwdParams bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.logit_lengths = logit_lengths;
+    bp.target_lengths = target_lengths;
+    bp.B = B; bp.T = T; bp.U = U; bp.H = H; bp.V = V;
+    bp.act_kind = act_kind;
+    bp.act_param = act_param;
+    bp.tT_log2 = jp.tT_log2; bp.nTt = jp.nTt; bp.nTu = jp.nTu;
+    bp.KB = jp.KB; bp.NVB = pl.NVB; bp.NT4 = pl.NT4;
+    bp.dY_img = jp.dY_img;
+    bp.J_img = jp.J_img;
+    bp.dpre_part = reinterpret_cast<float*>(ws + pl.dY_bytes + pl.J_bytes);
+    bp.dW_part = reinterpret_cast<float*>(ws + pl.dY_bytes + pl.J_bytes + pl.part_bytes);
+    bp.db_part = reinterpret_cast<float*>(ws + pl.dY_bytes + pl.J_bytes + pl.part_bytes + pl.dW_bytes);
+    bp.NVT = pl.NVT; bp.NHT = pl.NHT; bp.n_splits = pl.n_splits;
+    // h-splits of the dJ accumulator (<= 512 TMEM columns, single buffered): one split up to 5 h-blocks
+    if (jp.KB <= 5) { bp.n_hsplit = 1; bp.hs_kb[0] = 0; bp.hs_kb[1] = jp.KB; bp.hs_kb[2] = jp.KB; }
+    else { bp.n_hsplit = 2; bp.hs_kb[0] = 0; bp.hs_kb[1] = (jp.KB + 1) / 2; bp.hs_kb[2] = jp.KB; }
+
+    CUtensorMap tmap_fwd, tmap_dj;
+    if (int rc = make_tmap_2d_bf16(&tmap_fwd, W, (uint64_t)V, (uint64_t)H, kWStageK, kTileN, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    if (int rc = make_tmap_2d_bf16(&tmap_dj, W, (uint64_t)V, (uint64_t)H, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+
+    cudaError_t e;
+    e = cudaMemsetAsync(d_enc, 0, sizeof(float) * (size_t)B * T * H, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(d_enc)");
+    e = cudaMemsetAsync(d_dec, 0, sizeof(float) * (size_t)B * U * H, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(d_dec)");
+
+    const DjSmem djL = dj_smem_layout();
+    const DwSmem dwL = dw_smem_layout();
+    e = cudaFuncSetAttribute(dj_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)djL.total);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dj_gemm_kernel)");
+    e = cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dwL.total);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dw_gemm_kernel)");
+
+    const int total_tiles = B * jp.nTt * jp.nTu;
+    const int tU = 128 >> jp.tT_log2;
+    int chunk_idx = 0;
+    for (int t0 = 0; t0 < total_tiles; t0 += pl.chunk_tiles, ++chunk_idx) {
+        const int t1 = t0 + pl.chunk_tiles < total_tiles ? t0 + pl.chunk_tiles : total_tiles;
+        jp.tile_begin = bp.tile_begin = t0;
+        jp.tile_end = bp.tile_end = t1;
+        if (int rc = launch_joint<MODE_GRAD>(tmap_fwd, jp, sms, st)) return rc;
+
+        const int n_units = (t1 - t0) * bp.n_hsplit;
+        dj_gemm_kernel<<<n_units < sms ? n_units : sms, kBwdThreads, djL.total, st>>>(tmap_dj, bp);
+        ++g_launches;
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "dj_gemm_kernel launch");
+
+        const int g0 = t0 / jp.nTu, g1 = t1 / jp.nTu;
+        reduce_dpre_enc_kernel<<<g1 - g0, 256, 0, st>>>(bp, d_enc);
+        const int b0 = g0 / jp.nTt, b1 = (g1 - 1) / jp.nTt;
+        reduce_dpre_dec_kernel<<<dim3(jp.nTu, b1 - b0 + 1), 256, 0, st>>>(bp, d_dec);
+        g_launches += 2;
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "reduce_dpre kernels launch");
+
+        bp.accumulate = chunk_idx > 0;
+        dw_gemm_kernel<<<pl.NVT * pl.NHT * pl.n_splits, kBwdThreads, dwL.total, st>>>(bp);
+        ++g_launches;
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "dw_gemm_kernel launch");
+    }
+    (void)tU;
+    reduce_dw_kernel<<<sms * 2, 256, 0, st>>>(bp, dW, db);
+    ++g_launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "reduce_dw_kernel launch");
+    return TSASR_OK;
 }
+
+}  // extern "C"

@@ -1,2 +1,446 @@
-// placeholder, replaced below
+// backward_gemm.cuh -- the two backward GEMMs of the fused joint (tcgen05 + TMEM + TMA/bulk copies).
+//
+// They consume the operand images the MODE_GRAD pass of joint_gemm.cuh leaves in the (L2-sized)
+// chunk workspace: per 128-cell tile, dY images [v-block][128 cells x 64 v] and J images
+// [h-block][128 cells x 64 h], both bf16 in the SWIZZLE_128B shared-memory image, so a block is one
+// contiguous 16 KB bulk copy and is directly addressable by a UMMA descriptor -- K-major when the
+// 64-wide dimension is the contraction (dJ), MN-major when the 128 cells are the contraction (dW).
+//
+//   dj_gemm_kernel : dJ[cells, h] = sum_v dY[cells, v] * W[v, h]          (autograd of SB/nnet/linear.py:74)
+//                    epilogue: dpre = dJ * act'(J) (transducer_joint.py:95 backward) and the two
+//                    broadcast-sum reductions of transducer_joint.py:74 (sum over u -> d_enc rows,
+//                    sum over t -> d_dec rows) inside the tile; per-tile partial rows go to a small
+//                    buffer that reduce_dpre_* kernels fold deterministically.
+//   dw_gemm_kernel : dW[v, h] += sum_cells dY[cells, v] * J[cells, h], db[v] += sum_cells dY[cells, v]
+//                    (db rides along as 16 extra accumulator columns fed by a constant "ones" block).
 #pragma once
+
+#include <cuda.h>
+
+#include "common.cuh"
+#include "joint_gemm.cuh"
+
+namespace tsasr {
+
+static constexpr int kImgBytes = 16384;  // one [128 x 64] bf16 SWIZZLE_128B image
+static constexpr int kBwdThreads = 192;  // warp 0: loads, warp 1: MMA, warps 2-5: epilogue
+
+struct BwdParams {
+    const int* logit_lengths;
+    const int* target_lengths;
+    int B, T, U, H, V;
+    int act_kind;
+    float act_param;
+    int tT_log2, nTt, nTu;
+    int tile_begin, tile_end;
+    int KB;        // H / 64
+    int NVB;       // ceil(V / 64): v-blocks that carry data
+    int NT4;       // v-block images allocated per tile (4 * ceil(V / 256))
+    const __nv_bfloat16* dY_img;
+    const __nv_bfloat16* J_img;
+    // dJ
+    float* dpre_part;  // [tile - tile_begin][tT + tU][H]
+    int n_hsplit;      // 1 or 2
+    int hs_kb[3];      // split s covers h-blocks [hs_kb[s], hs_kb[s+1])
+    // dW
+    float* dW_part;    // [n_splits][NVT * 128][H]
+    float* db_part;    // [n_splits][NVT * 128]
+    int NVT;           // ceil(V / 128)
+    int NHT;           // h-tiles of up to 4 h-blocks
+    int n_splits;
+    int accumulate;    // 0: store, 1: read-modify-write (later chunks)
+};
+
+__device__ __forceinline__ bool tile_live(const BwdParams& p, int tile) {
+    const int per_b = p.nTt * p.nTu;
+    const int b = tile / per_b;
+    const int rem = tile - b * per_b;
+    const int tt = rem / p.nTu, tu = rem - tt * p.nTu;
+    return (tt << p.tT_log2) < p.logit_lengths[b] && tu * (kTileM >> p.tT_log2) < p.target_lengths[b] + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dJ GEMM + activation backward + in-tile broadcast-sum reductions
+// ------------------------------------------------------------------------------------------------
+static constexpr int kDjStages = 3;
+static constexpr int kDjStageBytes = kImgBytes + 5 * 8192;  // dY image + up to 5 W boxes [64 v x 64 h]
+static constexpr int kDjStagingFloats = 128 * 33;
+
+struct DjSmem { uint32_t stage_off, staging_off, bar_off, tmem_off, total; };
+__host__ __device__ inline DjSmem dj_smem_layout() {
+    DjSmem l;
+    l.stage_off = 0;
+    l.staging_off = kDjStages * kDjStageBytes;
+    l.bar_off = l.staging_off + 2 * kDjStagingFloats * 4;
+    l.tmem_off = l.bar_off + 16 * 8;
+    l.total = l.tmem_off + 16;
+    return l;
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const BwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const DjSmem L = dj_smem_layout();
+    float* staging = reinterpret_cast<float*>(smem + L.staging_off);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+    uint64_t* full = bars;             // [kDjStages]
+    uint64_t* empty = bars + 4;        // [kDjStages]
+    uint64_t* acc_full = bars + 8;
+    uint64_t* acc_empty = bars + 9;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
+    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) __trap();
+        for (int i = 0; i < kDjStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        fence_barrier_init();
+    }
+    if (warp_idx == 0 && lane == 0) tma_prefetch_desc(&tmap_w);
+    if (warp_idx == 1) tmem_alloc<512>(tmem_ptr);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int n_units = (p.tile_end - p.tile_begin) * p.n_hsplit;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+                const int tl = unit / p.n_hsplit, hs = unit - tl * p.n_hsplit;
+                if (!tile_live(p, p.tile_begin + tl)) continue;
+                const int hb0 = p.hs_kb[hs], nhb = p.hs_kb[hs + 1] - hb0;
+                const uint8_t* dy = reinterpret_cast<const uint8_t*>(p.dY_img) + (size_t)tl * p.NT4 * kImgBytes;
+                for (int vb = 0; vb < p.NVB; ++vb) {
+                    mbar_wait(&empty[stage], phase ^ 1, 0x700 | stage);
+                    uint8_t* st = smem + L.stage_off + stage * kDjStageBytes;
+                    mbar_arrive_expect_tx(&full[stage], kImgBytes + nhb * 8192);
+                    bulk_load_1d(st, dy + (size_t)vb * kImgBytes, kImgBytes, &full[stage]);
+                    for (int j = 0; j < nhb; ++j)
+                        tma_load_2d(st + kImgBytes + j * 8192, &tmap_w, &full[stage], (hb0 + j) * 64, vb * 64);
+                    if (++stage == kDjStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+                const int tl = unit / p.n_hsplit, hs = unit - tl * p.n_hsplit;
+                if (!tile_live(p, p.tile_begin + tl)) continue;
+                const int nhb = p.hs_kb[hs + 1] - p.hs_kb[hs];
+                const int n0 = nhb >= 4 ? 256 : nhb * 64, n1 = (nhb - 4) * 64;  // second MMA covers h-block 4
+                const uint32_t idesc0 = make_idesc_bf16(kTileM, n0, 0, 1);
+                const uint32_t idesc1 = make_idesc_bf16(kTileM, n1 > 0 ? n1 : 64, 0, 1);
+                mbar_wait(acc_empty, (it & 1) ^ 1, 0x800);
+                tcgen05_fence_after();
+                for (int vb = 0; vb < p.NVB; ++vb) {
+                    mbar_wait(&full[stage], phase, 0x900 | stage);
+                    tcgen05_fence_after();
+                    const uint32_t a_base = smem_u32(smem + L.stage_off + stage * kDjStageBytes);
+                    const uint32_t b_base = a_base + kImgBytes;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t a_desc = make_smem_desc_sw128(a_base + k * 32, 0, 1024);          // K-major
+                        const uint64_t b_desc = make_smem_desc_sw128(b_base + k * 2048, 8192, 1024);     // MN-major
+                        umma_bf16(tmem_base, a_desc, b_desc, idesc0, (vb | k) != 0);
+                        if (n1 > 0) {
+                            const uint64_t b_desc1 = make_smem_desc_sw128(b_base + 4 * 8192 + k * 2048, 8192, 1024);
+                            umma_bf16(tmem_base + 256, a_desc, b_desc1, idesc1, (vb | k) != 0);
+                        }
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == kDjStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(acc_full);
+                ++it;
+            }
+        }
+    } else {
+        const int q = warp_idx & 3;
+        const int row = q * 32 + lane;
+        const int e = threadIdx.x - 64;  // 0..127
+        const int col = e & 31, part = e >> 5;
+        const int tT = 1 << p.tT_log2, tU = kTileM >> p.tT_log2;
+        uint32_t it = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int tl = unit / p.n_hsplit, hs = unit - tl * p.n_hsplit;
+            if (!tile_live(p, p.tile_begin + tl)) continue;
+            const int h_begin = p.hs_kb[hs] * 64, n_h = (p.hs_kb[hs + 1] - p.hs_kb[hs]) * 64;
+            const uint8_t* jimg = reinterpret_cast<const uint8_t*>(p.J_img) + (size_t)tl * p.KB * kImgBytes;
+            float* part_out = p.dpre_part + (size_t)tl * (tT + tU) * p.H;
+            mbar_wait(acc_full, it & 1, 0xA00);
+            tcgen05_fence_after();
+            for (int cc = 0, ci = 0; cc < n_h; cc += 32, ++ci) {
+                uint32_t raw[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + cc, raw);
+                // activation outputs of this row: 32 bf16 = 4 chunks of the J image
+                const int h = h_begin + cc;
+                const uint8_t* jb = jimg + (size_t)(h >> 6) * kImgBytes;
+                uint4 jv[4];
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4)
+                    jv[c4] = *reinterpret_cast<const uint4*>(jb + sw128_offset((uint32_t)row, (uint32_t)(((h & 63) >> 3) + c4)));
+                tmem_ld_wait();
+                float* sbuf = staging + (ci & 1) * kDjStagingFloats;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(&jv[c4]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j = c4 * 8 + k * 2;
+                        sbuf[row * 33 + j] = __uint_as_float(raw[j]) * act_grad_from_output(bf16_lo(w[k]), p.act_kind, p.act_param);
+                        sbuf[row * 33 + j + 1] = __uint_as_float(raw[j + 1]) * act_grad_from_output(bf16_hi(w[k]), p.act_kind, p.act_param);
+                    }
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                // sum over ui (rows ui*tT + ti) -> d_enc partial row ti; sum over ti -> d_dec partial row ui
+                for (int ti = part; ti < tT; ti += 4) {
+                    float s = 0.f;
+                    for (int ui = 0; ui < tU; ++ui) s += sbuf[(ui * tT + ti) * 33 + col];
+                    part_out[(size_t)ti * p.H + h + col] = s;
+                }
+                for (int ui = part; ui < tU; ui += 4) {
+                    float s = 0.f;
+                    for (int ti = 0; ti < tT; ++ti) s += sbuf[(ui * tT + ti) * 33 + col];
+                    part_out[(size_t)(tT + ui) * p.H + h + col] = s;
+                }
+                // staging is double-buffered: the next chunk writes the other buffer, and the barrier of
+                // the next chunk orders these reads before that buffer is written again
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+            asm volatile("bar.sync 2, 128;" ::: "memory");  // staging buffers are free again
+            ++it;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// Fold the per-tile partial rows.  d_enc rows are complete inside one (b, tt) group of label tiles
+// (chunks are aligned to such groups) -> plain stores.  d_dec rows accumulate over tt, across chunks.
+__global__ void reduce_dpre_enc_kernel(const BwdParams p, float* __restrict__ d_enc) {
+    const int tT = 1 << p.tT_log2, tU = kTileM >> p.tT_log2;
+    const int g = p.tile_begin / p.nTu + blockIdx.x;  // global (b, tt) group
+    const int b = g / p.nTt, tt = g - b * p.nTt;
+    const int Tb = p.logit_lengths[b], Ub = p.target_lengths[b] + 1;
+    const int t0 = tt * tT;
+    if (t0 >= Tb) return;
+    const int n_tu = (Ub + tU - 1) / tU;  // live label tiles
+    const float* base = p.dpre_part + (size_t)(g * p.nTu - p.tile_begin) * (tT + tU) * p.H;
+    for (int i = threadIdx.x; i < tT * p.H; i += blockDim.x) {
+        const int ti = i / p.H, h = i - ti * p.H;
+        if (t0 + ti >= p.T) continue;
+        float s = 0.f;
+        for (int tu = 0; tu < n_tu; ++tu) s += base[((size_t)tu * (tT + tU) + ti) * p.H + h];
+        d_enc[((size_t)b * p.T + t0 + ti) * p.H + h] = s;
+    }
+}
+
+__global__ void reduce_dpre_dec_kernel(const BwdParams p, float* __restrict__ d_dec) {
+    const int tT = 1 << p.tT_log2, tU = kTileM >> p.tT_log2;
+    const int g_begin = p.tile_begin / p.nTu, g_end = p.tile_end / p.nTu;
+    const int b = g_begin / p.nTt + blockIdx.y;
+    const int tu = blockIdx.x;
+    const int Tb = p.logit_lengths[b], Ub = p.target_lengths[b] + 1;
+    if (tu * tU >= Ub) return;
+    const int gb0 = max(g_begin, b * p.nTt), gb1 = min(g_end, (b + 1) * p.nTt);
+    for (int i = threadIdx.x; i < tU * p.H; i += blockDim.x) {
+        const int ui = i / p.H, h = i - ui * p.H;
+        const int u = tu * tU + ui;
+        if (u >= p.U) continue;
+        float s = 0.f;
+        for (int g = gb0; g < gb1; ++g) {
+            const int tt = g - b * p.nTt;
+            if (tt * tT >= Tb) break;
+            s += p.dpre_part[((size_t)(g * p.nTu + tu - p.tile_begin) * (tT + tU) + tT + ui) * p.H + h];
+        }
+        d_dec[((size_t)b * p.U + u) * p.H + h] += s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dW / db GEMM (contraction over cells), split-K over the chunk's tiles
+// ------------------------------------------------------------------------------------------------
+static constexpr int kDwStages = 2;
+static constexpr int kDwStageBytes = 6 * kImgBytes;  // 2 dY v-block images + up to 4 J h-block images
+
+struct DwSmem { uint32_t stage_off, ones_off, bar_off, tmem_off, total; };
+__host__ __device__ inline DwSmem dw_smem_layout() {
+    DwSmem l;
+    l.stage_off = 0;
+    l.ones_off = kDwStages * kDwStageBytes;
+    l.bar_off = l.ones_off + kImgBytes;
+    l.tmem_off = l.bar_off + 8 * 8;
+    l.total = l.tmem_off + 16;
+    return l;
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+dw_gemm_kernel(const BwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const DwSmem L = dw_smem_layout();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+    uint64_t* full = bars;        // [2]
+    uint64_t* empty = bars + 2;   // [2]
+    uint64_t* acc_full = bars + 4;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
+    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // unit = (v-tile, h-tile, split)
+    const int unit = blockIdx.x;
+    const int split = unit % p.n_splits;
+    const int ht = (unit / p.n_splits) % p.NHT;
+    const int vt = unit / (p.n_splits * p.NHT);
+    const int hb0 = ht * 4, nhb = min(4, p.KB - hb0);
+    const int nvb = min(2, p.NVB - vt * 2);          // v-block images that exist for this v-tile
+    const bool with_db = ht == p.NHT - 1;            // the last h-tile also carries the bias gradient
+    const int n_tiles = p.tile_end - p.tile_begin;
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) __trap();
+        for (int i = 0; i < kDwStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    // constant "ones" B block: J-image layout with column h = 0 set to 1.0 for all 128 cells
+    {
+        uint4* o = reinterpret_cast<uint4*>(smem + L.ones_off);
+        for (int i = threadIdx.x; i < kImgBytes / 16; i += blockDim.x) o[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        if (threadIdx.x < 128)
+            *reinterpret_cast<uint16_t*>(smem + L.ones_off + sw128_offset(threadIdx.x, 0)) = 0x3F80;  // bf16 1.0
+        fence_proxy_async_smem();
+    }
+    if (warp_idx == 1) tmem_alloc<512>(tmem_ptr);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tl = split; tl < n_tiles; tl += p.n_splits) {
+                if (!tile_live(p, p.tile_begin + tl)) continue;
+                mbar_wait(&empty[stage], phase ^ 1, 0xB00 | stage);
+                uint8_t* st = smem + L.stage_off + stage * kDwStageBytes;
+                const uint8_t* dy = reinterpret_cast<const uint8_t*>(p.dY_img) + ((size_t)tl * p.NT4 + vt * 2) * kImgBytes;
+                const uint8_t* jm = reinterpret_cast<const uint8_t*>(p.J_img) + ((size_t)tl * p.KB + hb0) * kImgBytes;
+                mbar_arrive_expect_tx(&full[stage], (2 + nhb) * kImgBytes);
+                bulk_load_1d(st, dy, kImgBytes, &full[stage]);
+                // a v-tile whose second 64-column block lies beyond V re-reads the first block: those
+                // accumulator rows (v >= V) are never stored
+                bulk_load_1d(st + kImgBytes, dy + (nvb == 2 ? kImgBytes : 0), kImgBytes, &full[stage]);
+                bulk_load_1d(st + 2 * kImgBytes, jm, nhb * kImgBytes, &full[stage]);
+                if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp_idx == 1) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            bool first = true;
+            const uint32_t idesc = make_idesc_bf16(kTileM, nhb * 64, 1, 1);
+            const uint32_t idesc_db = make_idesc_bf16(kTileM, 16, 1, 1);
+            const uint32_t ones_base = smem_u32(smem + L.ones_off);
+            for (int tl = split; tl < n_tiles; tl += p.n_splits) {
+                if (!tile_live(p, p.tile_begin + tl)) continue;
+                mbar_wait(&full[stage], phase, 0xC00 | stage);
+                tcgen05_fence_after();
+                const uint32_t a_base = smem_u32(smem + L.stage_off + stage * kDwStageBytes);
+                const uint32_t b_base = a_base + 2 * kImgBytes;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {  // 16 cells per step = two 8-row groups of the image
+                    const uint64_t a_desc = make_smem_desc_sw128(a_base + k * 2048, kImgBytes, 1024);  // MN-major, M = v
+                    const uint64_t b_desc = make_smem_desc_sw128(b_base + k * 2048, kImgBytes, 1024);  // MN-major, N = h
+                    umma_bf16(tmem_base, a_desc, b_desc, idesc, !(first && k == 0));
+                    if (with_db) {
+                        const uint64_t o_desc = make_smem_desc_sw128(ones_base + k * 2048, kImgBytes, 1024);
+                        umma_bf16(tmem_base + 256, a_desc, o_desc, idesc_db, !(first && k == 0));
+                    }
+                }
+                first = false;
+                umma_commit(&empty[stage]);
+                if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        const int q = warp_idx & 3;
+        const int row = q * 32 + lane;
+        const int v = vt * 128 + row;
+        // did this split see any live tile?  (all roles agree; the epilogue must not wait otherwise)
+        bool any = false;
+        for (int tl = split; tl < n_tiles; tl += p.n_splits) any |= tile_live(p, p.tile_begin + tl);
+        const size_t vrows = (size_t)p.NVT * 128;
+        float* wrow = p.dW_part + ((size_t)split * vrows + v) * p.H + hb0 * 64;
+        if (any) {
+            mbar_wait(acc_full, 0, 0xD00);
+            tcgen05_fence_after();
+        }
+        for (int cc = 0; cc < nhb * 64; cc += 32) {
+            uint32_t raw[32];
+            if (any) {
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + cc, raw);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) raw[j] = 0u;
+            }
+            float4* dst = reinterpret_cast<float4*>(wrow + cc);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 x = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                       __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+                if (p.accumulate) {
+                    const float4 o = dst[j];
+                    x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
+                }
+                dst[j] = x;
+            }
+        }
+        if (with_db) {
+            uint32_t raw[32];
+            float x = 0.f;
+            if (any) {
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + 256, raw);
+                tmem_ld_wait();
+                x = __uint_as_float(raw[0]);
+            }
+            float* d = p.db_part + (size_t)split * vrows + v;
+            *d = p.accumulate ? *d + x : x;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+__global__ void reduce_dw_kernel(const BwdParams p, float* __restrict__ dW, float* __restrict__ db) {
+    const size_t vrows = (size_t)p.NVT * 128;
+    const size_t n = (size_t)p.V * p.H;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int sp = 0; sp < p.n_splits; ++sp) s += p.dW_part[(size_t)sp * vrows * p.H + i];
+        dW[i] = s;
+    }
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < (size_t)p.V; v += (size_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int sp = 0; sp < p.n_splits; ++sp) s += p.db_part[(size_t)sp * vrows + v];
+        db[v] = s;
+    }
+}
+
+}  // namespace tsasr

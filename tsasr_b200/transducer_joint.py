@@ -24,7 +24,7 @@ from . import _lib
 
 logger = logging.getLogger(__name__)
 
-_MIN_DEFERRED_CELLS = 64  # below this (decode-time shapes) the eager math is used
+_MIN_DEFERRED_CELLS = 2  # a single cell (decode-time [B,1,1,H] calls) uses the eager math
 
 
 def activation_code(module):
