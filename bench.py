@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- lattice cells/s of the fused joint + RNN-T loss forward+backward (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one forward+backward pass of the hot path over one batch of synthetic input:
+joint("sum") + activation + head Linear + log-softmax + RNN-T loss, gradients w.r.t. enc_out,
+dec_out, W, b (BASELINE configs[1]: B=16, T=400, U=100, V=1000, H=640, bf16 joint / fp32 lattice).
+At N > 1 every rank runs the same per-GPU batch (utterance sharding, weak scaling, global batch
+16*N = 128 at N=8) and the step ends with one NCCL all-reduce of {dW, db, loss}.
+
+Prints ONE JSON line (rank 0).  ``value`` is device-timed with inputs resident in HBM; ``e2e`` goes
+through the public drop-in modules with pinned HOST buffers (H2D + D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(B=16, T=400, U=100, V=1000, H=640, act="leaky_relu", act_param=0.01, blank=0)
+CPU_SAMPLE = dict(B=4, T=200, U=40, V=1000, H=640)  # BASELINE configs[0] shape: ~2 s per CPU step
+METRIC = "lattice cells/sec (B*T*U) joint+RNN-T fwd+bwd"
+UNIT = "cells/s"
+
+
+def synth(cfg, device, seed=0):
+    """Synthetic inputs of SURVEY.md section 8d: enc/dec ~ 0.5*randn, W/b ~ nn.Linear init, full lengths."""
+    g = torch.Generator().manual_seed(seed)
+    B, T, U, V, H = (cfg[k] for k in "BTUVH")
+    enc = 0.5 * torch.randn(B, T, H, generator=g)
+    dec = 0.5 * torch.randn(B, U, H, generator=g)
+    bound = 1.0 / H ** 0.5
+    W = (torch.rand(V, H, generator=g) * 2 - 1) * bound
+    b = (torch.rand(V, generator=g) * 2 - 1) * bound
+    targets = torch.randint(1, V, (B, U - 1), generator=g, dtype=torch.int32)
+    ll = torch.full((B,), T, dtype=torch.int32)
+    tl = torch.full((B,), U - 1, dtype=torch.int32)
+    return [x.to(device) for x in (enc, dec, W, b, targets, ll, tl)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 6:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json, bf16 sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_step(sample, threads):
+    """The reference's CPU path for this hot path: torch eager joint + Linear + torchaudio rnnt_loss
+    (what SB/nnet/losses.py:72-79 calls) + backward, restated in oracle/reference_chain.py."""
+    from oracle.reference_chain import reference_joint_loss_fwd_bwd
+
+    enc, dec, W, b, targets, ll, tl = synth(sample, "cpu", seed=1)
+    torch.set_num_threads(threads)
+    best = None
+    for i in range(4):  # 1 warm-up + best of 3
+        t0 = time.perf_counter()
+        reference_joint_loss_fwd_bwd(enc, dec, W, b, targets, ll, tl, 0, "leaky_relu", 0.01, round_bf16=False, reduction="mean")
+        dt = time.perf_counter() - t0
+        if i > 0:
+            best = dt if best is None else min(best, dt)
+    return sample["B"] * sample["T"] * sample["U"] / best, best
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = max(1, args.steps)
+    from oracle.reference_chain import reference_joint_loss_fwd_bwd
+
+    sample = CPU_SAMPLE
+    enc, dec, W, b, targets, ll, tl = synth(sample, "cpu", seed=1)
+    torch.set_num_threads(threads)
+    for _ in range(max(1, min(args.warmup, 2))):
+        reference_joint_loss_fwd_bwd(enc, dec, W, b, targets, ll, tl, 0, "leaky_relu", 0.01, reduction="mean")
+    times = []
+    for _ in range(min(steps, 10)):
+        t0 = time.perf_counter()
+        reference_joint_loss_fwd_bwd(enc, dec, W, b, targets, ll, tl, 0, "leaky_relu", 0.01, reduction="mean")
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    value = sample["B"] * sample["T"] * sample["U"] / (ms / 1e3)
+    sample_txt = ("torch eager Transducer_joint(sum,LeakyReLU)+Linear + torchaudio.functional.rnnt_loss CPU + backward "
+                  "(the libraries the reference calls, chain restated in oracle/reference_chain.py); bounded sample "
+                  f"B={sample['B']},T={sample['T']},U={sample['U']},V={sample['V']},H={sample['H']} fp32 of the config workload")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(), "cpu_sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample_txt},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_name():
+    return ("conformer-t_scratch joint+RNN-T loss fwd+bwd, synthetic B=16 T=400 U=100 V=1000 H=640 per GPU, "
+            "bf16 joint / fp32 lattice (BASELINE configs[1]; configs[2] at N>1)")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import tsasr_b200
+    from tsasr_b200 import _lib, ops
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (tsasr_b200 has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    W_steps = max(3, args.warmup)
+    K = max(1, args.steps)
+
+    cfg = CFG
+    B, T, U, V, H = (cfg[k] for k in "BTUVH")
+    cells = B * T * U
+    enc, dec, Wt, bias, targets, ll, tl = synth(cfg, dev, seed=rank)
+    enc16, dec16, W16 = enc.bfloat16().contiguous(), dec.bfloat16().contiguous(), Wt.bfloat16().contiguous()
+    dcost = torch.full((B,), 1.0 / (B * world), dtype=torch.float32, device=dev)
+    act = _lib.ACT_CODES[cfg["act"]]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    comm = torch.empty(V * H + V + 1, dtype=torch.float32, device=dev)
+
+    fwd_ev = []
+
+    def step(record):
+        """One fwd+bwd pass; inputs already resident in HBM (bf16 operands, fp32 bias)."""
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        lat2, logz = ops.joint_fwd(enc16, dec16, W16, bias, targets, ll, tl, cfg["blank"], act, cfg["act_param"])
+        if record:
+            e1.record()
+            fwd_ev.append((e0, e1))
+        alpha, beta, cost, _, _ = ops.alpha_beta(lat2, ll, tl, B, T, U)
+        d_enc, d_dec, dW, db = ops.joint_bwd(enc16, dec16, W16, bias, targets, ll, tl, cfg["blank"], act, cfg["act_param"],
+                                             lat2, logz, alpha, beta, cost, dcost)
+        if dist is not None:
+            comm[: V * H].copy_(dW.view(-1))
+            comm[V * H: V * H + V].copy_(db)
+            comm[-1] = cost.sum() / (B * world)
+            dist.all_reduce(comm)
+        return cost
+
+    for _ in range(W_steps):
+        flush.zero_()
+        step(False)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _lib.launch_count()
+    evs = []
+    for _ in range(K):
+        flush.zero_()  # L2 flush between timed iterations (untimed)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step(True)
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    total_ms = sum(s.elapsed_time(e) for s, e in evs)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = t.item()
+    ms_per_step = total_ms / K
+    value = world * cells / (ms_per_step / 1e3)
+    fwd_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in fwd_ev)
+
+    # ---- e2e: public drop-in modules, pinned host inputs, H2D + D2H inside the timed region ----
+    joiner = tsasr_b200.Transducer_joint(joint="sum", nonlinearity=torch.nn.LeakyReLU)
+    head = torch.nn.Linear(H, V).to(dev)
+    with torch.no_grad():
+        head.weight.copy_(Wt)
+        head.bias.copy_(bias)
+    h_enc, h_dec = enc.cpu().pin_memory(), dec.cpu().pin_memory()
+    h_tg = targets.cpu().long().pin_memory()
+    h_il, h_tl = torch.ones(B).pin_memory(), torch.ones(B).pin_memory()  # relative lengths (SpeechBrain convention)
+    h2d = sum(x.numel() * x.element_size() for x in (h_enc, h_dec, h_tg, h_il, h_tl))
+
+    def e2e_step():
+        e_ = h_enc.to(dev, non_blocking=True).requires_grad_()
+        d_ = h_dec.to(dev, non_blocking=True).requires_grad_()
+        tg_, il_, tl_ = (x.to(dev, non_blocking=True) for x in (h_tg, h_il, h_tl))
+        logits = head(joiner(e_[..., None, :], d_[:, None, ...]))  # train_librispeechmix_scratch.py:132,135
+        loss = tsasr_b200.transducer_loss(logits, tg_, il_, tl_, blank_index=0, reduction="mean", use_torchaudio=True)
+        loss.backward()
+        if dist is not None:
+            for p in head.parameters():
+                dist.all_reduce(p.grad)
+        head.zero_grad(set_to_none=True)
+        return loss.item()  # D2H read of the step's result
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e2e_ms = 0.0
+    Ke = min(K, 10)
+    for _ in range(Ke):
+        flush.zero_()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        loss_val = e2e_step()
+        e.record()
+        torch.cuda.synchronize()
+        e2e_ms += s.elapsed_time(e)
+    t = torch.tensor([e2e_ms / Ke], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * cells / (t.item() / 1e3)
+
+    out = None
+    if rank == 0:
+        peak_tf, peak_hbm, peak_src = measured_peaks()
+        flops = 2.0 * cells * H * V  # algorithmic FLOPs of the forward joint GEMM launch
+        achieved = flops / (fwd_ms / 1e3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("joint_gemm_kernel_fwd_dram_bytes_per_launch")
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_steps,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(), "B_per_gpu": B, "T": T, "U": U, "V": V, "H": H,
+                       "lengths": "full", "activation": cfg["act"], "parallelism": f"utterance-sharded dp{world}",
+                       "l2": "flushed between timed steps with a 256 MiB write (untimed); step timed with CUDA events"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "api": "Transducer_joint -> nn.Linear head -> transducer_loss(handle) -> backward, fp32 pinned host inputs",
+                    "loss": loss_val},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "joint_gemm_kernel<MODE_FWD> (tcgen05 joint GEMM + online log-softmax)", "bound": "tensor",
+                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": fwd_ms,
+                         "algorithmic_flops_per_launch": flops,
+                         "step_frac_of_6MHV_roofline": (6.0 * cells * H * V / (ms_per_step / 1e3) / 1e12) / peak_tf},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, secs = cpu_reference_step(CPU_SAMPLE, threads)
+            out["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": threads, "kind": "reference",
+                "sample": ("torch eager joint+Linear + torchaudio.functional.rnnt_loss CPU + backward (the reference's CPU path, "
+                           f"oracle/reference_chain.py) on B={CPU_SAMPLE['B']},T={CPU_SAMPLE['T']},U={CPU_SAMPLE['U']},V={CPU_SAMPLE['V']},"
+                           f"H={CPU_SAMPLE['H']} fp32, 1 warm-up + best of 3 ({secs:.2f} s/step)")}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
