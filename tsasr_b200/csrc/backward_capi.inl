@@ -9,6 +9,8 @@
 
 namespace {
 
+static constexpr size_t kDefaultChunkBytes = (size_t)3 << 30;  // 3 GiB of operand images per chunk
+
 struct BwdPlan {
     int chunk_tiles;      // multiple of nTu
     int n_chunks;
@@ -22,15 +24,25 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static void plan_bwd(const JointParams& jp, int num_sms, long long max_chunk_cells, BwdPlan* pl) {
     const int tT = 1 << jp.tT_log2, tU = 128 >> jp.tT_log2;
     const int total_tiles = jp.B * jp.nTt * jp.nTu;
-    long long want_tiles = max_chunk_cells > 0 ? max_chunk_cells / 128 : (long long)num_sms;
+    pl->NVB = (jp.V + 63) / 64;
+    pl->NT4 = jp.NT * 4;
+    // Default chunk: as many tiles as fit kDefaultChunkBytes of operand images (one chunk for
+    // BASELINE config 2).  The images are written once and read back while still warm in the 126 MB
+    // L2 by CTAs that work on the same tile at the same time; what spills goes to HBM at ~1x volume.
+    const size_t tile_bytes = (size_t)(pl->NT4 + jp.KB) * kImgBytes + (size_t)(tT + tU) * jp.H * 4;
+    long long want_tiles = max_chunk_cells > 0 ? max_chunk_cells / 128 : (long long)(kDefaultChunkBytes / tile_bytes);
     if (want_tiles < 1) want_tiles = 1;
-    int groups = (int)((want_tiles + jp.nTu - 1) / jp.nTu);
+    int groups = (int)(want_tiles / jp.nTu);
     if (groups < 1) groups = 1;
     pl->chunk_tiles = groups * jp.nTu;
     if (pl->chunk_tiles > total_tiles) pl->chunk_tiles = total_tiles;
     pl->n_chunks = (total_tiles + pl->chunk_tiles - 1) / pl->chunk_tiles;
-    pl->NVB = (jp.V + 63) / 64;
-    pl->NT4 = jp.NT * 4;
+    // balance the chunks (same count, equal sizes up to one group)
+    {
+        const int total_groups = total_tiles / jp.nTu;
+        const int gpc = (total_groups + pl->n_chunks - 1) / pl->n_chunks;
+        pl->chunk_tiles = gpc * jp.nTu;
+    }
     pl->NVT = (jp.V + 127) / 128;
     pl->NHT = (jp.KB + 3) / 4;
     int splits = num_sms / (pl->NVT * pl->NHT);
@@ -155,10 +167,8 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
         ++g_launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "dj_gemm_kernel launch");
 
-        const int g0 = t0 / jp.nTu, g1 = t1 / jp.nTu;
-        reduce_dpre_enc_kernel<<<g1 - g0, 256, 0, st>>>(bp, d_enc);
-        const int b0 = g0 / jp.nTt, b1 = (g1 - 1) / jp.nTt;
-        reduce_dpre_dec_kernel<<<dim3(jp.nTu, b1 - b0 + 1), 256, 0, st>>>(bp, d_dec);
+        reduce_dpre_enc_kernel<<<sms * 8, 256, 0, st>>>(bp, d_enc);
+        reduce_dpre_dec_kernel<<<sms * 8, 256, 0, st>>>(bp, d_dec);
         g_launches += 2;
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "reduce_dpre kernels launch");
 

@@ -226,42 +226,47 @@ dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const BwdParams p) {
     }
 }
 
-// Fold the per-tile partial rows.  d_enc rows are complete inside one (b, tt) group of label tiles
-// (chunks are aligned to such groups) -> plain stores.  d_dec rows accumulate over tt, across chunks.
-__global__ void reduce_dpre_enc_kernel(const BwdParams p, float* __restrict__ d_enc) {
+// Fold the per-tile partial rows (flat, h-contiguous, one thread per output element).  d_enc rows are
+// complete inside one (b, tt) group of label tiles (chunks are aligned to such groups) -> plain
+// stores.  d_dec rows accumulate over tt inside the chunk and, by read-modify-write, across chunks.
+__global__ void __launch_bounds__(256)
+reduce_dpre_enc_kernel(const BwdParams p, float* __restrict__ d_enc) {
     const int tT = 1 << p.tT_log2, tU = kTileM >> p.tT_log2;
-    const int g = p.tile_begin / p.nTu + blockIdx.x;  // global (b, tt) group
-    const int b = g / p.nTt, tt = g - b * p.nTt;
-    const int Tb = p.logit_lengths[b], Ub = p.target_lengths[b] + 1;
-    const int t0 = tt * tT;
-    if (t0 >= Tb) return;
-    const int n_tu = (Ub + tU - 1) / tU;  // live label tiles
-    const float* base = p.dpre_part + (size_t)(g * p.nTu - p.tile_begin) * (tT + tU) * p.H;
-    for (int i = threadIdx.x; i < tT * p.H; i += blockDim.x) {
-        const int ti = i / p.H, h = i - ti * p.H;
-        if (t0 + ti >= p.T) continue;
+    const int g_begin = p.tile_begin / p.nTu, n_groups = (p.tile_end - p.tile_begin) / p.nTu;
+    const long long total = (long long)n_groups * tT * p.H;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+        const int h = (int)(o % p.H);
+        const int ti = (int)((o / p.H) % tT);
+        const int gl = (int)(o / ((long long)p.H * tT));
+        const int g = g_begin + gl;
+        const int b = g / p.nTt, tt = g - b * p.nTt;
+        const int t = tt * tT + ti;
+        if (t >= p.logit_lengths[b]) continue;  // rows beyond T_b stay zero (memset)
+        const int n_tu = (p.target_lengths[b] + 1 + tU - 1) / tU;  // live label tiles
+        const float* base = p.dpre_part + ((size_t)gl * p.nTu * (tT + tU) + ti) * p.H + h;
         float s = 0.f;
-        for (int tu = 0; tu < n_tu; ++tu) s += base[((size_t)tu * (tT + tU) + ti) * p.H + h];
-        d_enc[((size_t)b * p.T + t0 + ti) * p.H + h] = s;
+        for (int tu = 0; tu < n_tu; ++tu) s += base[(size_t)tu * (tT + tU) * p.H];
+        d_enc[((size_t)b * p.T + t) * p.H + h] = s;
     }
 }
 
-__global__ void reduce_dpre_dec_kernel(const BwdParams p, float* __restrict__ d_dec) {
+__global__ void __launch_bounds__(256)
+reduce_dpre_dec_kernel(const BwdParams p, float* __restrict__ d_dec) {
     const int tT = 1 << p.tT_log2, tU = kTileM >> p.tT_log2;
     const int g_begin = p.tile_begin / p.nTu, g_end = p.tile_end / p.nTu;
-    const int b = g_begin / p.nTt + blockIdx.y;
-    const int tu = blockIdx.x;
-    const int Tb = p.logit_lengths[b], Ub = p.target_lengths[b] + 1;
-    if (tu * tU >= Ub) return;
-    const int gb0 = max(g_begin, b * p.nTt), gb1 = min(g_end, (b + 1) * p.nTt);
-    for (int i = threadIdx.x; i < tU * p.H; i += blockDim.x) {
-        const int ui = i / p.H, h = i - ui * p.H;
-        const int u = tu * tU + ui;
-        if (u >= p.U) continue;
+    const int b_begin = g_begin / p.nTt, b_end = (g_end - 1) / p.nTt + 1;
+    const long long total = (long long)(b_end - b_begin) * p.U * p.H;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+        const int h = (int)(o % p.H);
+        const int u = (int)((o / p.H) % p.U);
+        const int b = b_begin + (int)(o / ((long long)p.H * p.U));
+        const int Tb = p.logit_lengths[b];
+        if (u >= p.target_lengths[b] + 1) continue;
+        const int tu = u / tU, ui = u - tu * tU;
+        const int gb0 = max(g_begin, b * p.nTt), gb1 = min(g_end, (b + 1) * p.nTt);
         float s = 0.f;
         for (int g = gb0; g < gb1; ++g) {
-            const int tt = g - b * p.nTt;
-            if (tt * tT >= Tb) break;
+            if ((g - b * p.nTt) * tT >= Tb) break;  // dead frame tiles carry no data
             s += p.dpre_part[((size_t)(g * p.nTu + tu - p.tile_begin) * (tT + tU) + tT + ui) * p.H + h];
         }
         d_dec[((size_t)b * p.U + u) * p.H + h] += s;
