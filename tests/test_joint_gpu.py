@@ -93,7 +93,7 @@ GRAD_REL = 1e-2  # operand gradients: bf16 dlogits/J operands (2^-9 relative eac
 
 def _choose_tile_log2(T, U):
     best, best_l = -1, 4
-    for l in range(3, 8):
+    for l in range(3, 6):
         tT, tU = 1 << l, 128 >> l
         padded = ((T + tT - 1) // tT) * tT * ((U + tU - 1) // tU) * tU
         if best < 0 or padded < best or (padded == best and l == 4):

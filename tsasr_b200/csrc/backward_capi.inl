@@ -136,8 +136,9 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
     if (jp.KB <= 5) { bp.n_hsplit = 1; bp.hs_kb[0] = 0; bp.hs_kb[1] = jp.KB; bp.hs_kb[2] = jp.KB; }
     else { bp.n_hsplit = 2; bp.hs_kb[0] = 0; bp.hs_kb[1] = (jp.KB + 1) / 2; bp.hs_kb[2] = jp.KB; }
 
-    CUtensorMap tmap_fwd, tmap_dj;
-    if (int rc = make_tmap_2d_bf16(&tmap_fwd, W, (uint64_t)V, (uint64_t)H, kWStageK, kTileN, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    JointMaps maps;
+    if (int rc = make_joint_maps(&maps, jp, enc, dec, W)) return rc;
+    CUtensorMap tmap_dj;
     if (int rc = make_tmap_2d_bf16(&tmap_dj, W, (uint64_t)V, (uint64_t)H, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
 
     cudaError_t e;
@@ -160,7 +161,7 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
         const int t1 = t0 + pl.chunk_tiles < total_tiles ? t0 + pl.chunk_tiles : total_tiles;
         jp.tile_begin = bp.tile_begin = t0;
         jp.tile_end = bp.tile_end = t1;
-        if (int rc = launch_joint<MODE_GRAD>(tmap_fwd, jp, sms, st)) return rc;
+        if (int rc = launch_joint<MODE_GRAD>(maps, jp, sms, st)) return rc;
 
         const int n_units = (t1 - t0) * bp.n_hsplit;
         dj_gemm_kernel<<<n_units < sms ? n_units : sms, kBwdThreads, djL.total, st>>>(tmap_dj, bp);

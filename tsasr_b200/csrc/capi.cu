@@ -11,6 +11,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "backward_gemm.cuh"
@@ -110,11 +111,11 @@ static int device_info(int* num_sms, int* max_smem) {
     return TSASR_OK;
 }
 
-// ---- tile-shape selection: (tT, tU) with tT * tU = 128, tT >= 8, minimising padded cells ----
+// ---- tile-shape selection: (tT, tU) with tT * tU = 128, tT in {8,16,32}, minimising padded cells ----
 static void choose_tile(int T, int U, int* tT_log2) {
     long long best = -1;
     int best_l = 4;
-    for (int l = 3; l <= 7; ++l) {
+    for (int l = 3; l <= 5; ++l) {
         const int tT = 1 << l, tU = 128 >> l;
         const long long padded = (long long)((T + tT - 1) / tT) * tT * (long long)((U + tU - 1) / tU) * tU;
         // prefer tT = 16 on ties (d_enc partial sums stay in registers across label tiles)
@@ -132,8 +133,6 @@ static int fill_joint_params(JointParams& p, const void* enc, const void* dec, c
     REQUIRE((reinterpret_cast<uintptr_t>(enc) & 15) == 0 && (reinterpret_cast<uintptr_t>(dec) & 15) == 0,
             "enc/dec must be 16-byte aligned");
     memset(&p, 0, sizeof(p));
-    p.enc = static_cast<const __nv_bfloat16*>(enc);
-    p.dec = static_cast<const __nv_bfloat16*>(dec);
     p.bias = bias;
     p.targets = targets;
     p.logit_lengths = ll;
@@ -151,25 +150,60 @@ static int fill_joint_params(JointParams& p, const void* enc, const void* dec, c
     p.NT = (V + kTileN - 1) / kTileN;
     p.n_last = ((V - (p.NT - 1) * kTileN) + 15) / 16 * 16;
     int ns = kMaxWStages;
+    if (const char* env = getenv("TSASR_DEBUG_W_STAGES")) {  // development knob (pipeline-depth experiments)
+        const int v = atoi(env);
+        if (v >= 2 && v <= kMaxWStages) ns = v;
+    }
     while (ns > 2 && (int)smem_layout(p.KB, ns).total > max_smem) --ns;
     if ((int)smem_layout(p.KB, ns).total > max_smem)
         return fail(TSASR_E_UNSUPPORTED, "not enough shared memory (%d B) for H=%d", max_smem, H);
     p.num_w_stages = ns;
+    p.num_slice_slots = kSliceRingBytes / ((tT + tU) * 128);
+    return TSASR_OK;
+}
+
+struct JointMaps { CUtensorMap w, enc, dec; };
+
+// W [V,H]: 64-byte swizzled k-slices of 256 rows; enc [B*T,H] / dec [B*U,H]: plain [rows x 64] slices
+static int make_joint_maps(JointMaps* m, const JointParams& p, const void* enc, const void* dec, const void* W) {
+    const int tT = 1 << p.tT_log2, tU = 128 >> p.tT_log2;
+    if (int rc = make_tmap_2d_bf16(&m->w, W, (uint64_t)p.V, (uint64_t)p.H, kWStageK, kTileN, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    if (int rc = make_tmap_2d_bf16(&m->enc, enc, (uint64_t)p.B * p.T, (uint64_t)p.H, kABlockK, tT, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+    if (int rc = make_tmap_2d_bf16(&m->dec, dec, (uint64_t)p.B * p.U, (uint64_t)p.H, kABlockK, tU, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
     return TSASR_OK;
 }
 
 template <int MODE>
-static int launch_joint(const CUtensorMap& tmap, const JointParams& p, int num_sms, cudaStream_t st) {
+static int launch_joint(const JointMaps& maps, const JointParams& p, int num_sms, cudaStream_t st) {
     const SmemLayout L = smem_layout(p.KB, p.num_w_stages);
     cudaError_t e = cudaFuncSetAttribute(joint_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(joint_gemm_kernel)");
     const int tiles = p.tile_end - p.tile_begin;
     const int grid = tiles < num_sms ? tiles : num_sms;
     if (grid <= 0) return TSASR_OK;
-    joint_gemm_kernel<MODE><<<grid, kNumThreads, L.total, st>>>(tmap, p);
+    static const bool prof_on = getenv("TSASR_DEBUG_PROF") != nullptr;  // development: MMA-lane wait breakdown
+    JointParams pp = p;
+    long long* d_prof = nullptr;
+    if (prof_on) {
+        cudaMalloc(&d_prof, sizeof(long long) * 8 * grid);
+        cudaMemset(d_prof, 0, sizeof(long long) * 8 * grid);
+        pp.prof = d_prof;
+    }
+    joint_gemm_kernel<MODE><<<grid, kNumThreads, L.total, st>>>(maps.w, maps.enc, maps.dec, pp);
     ++g_launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "joint_gemm_kernel launch");
+    if (prof_on) {
+        cudaStreamSynchronize(st);
+        long long* h = new long long[8 * grid];
+        cudaMemcpy(h, d_prof, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
+        double tot = 0, acc = 0, a = 0, w = 0, tiles = 0;
+        for (int i = 0; i < grid; ++i) { tot += h[8 * i]; acc += h[8 * i + 1]; a += h[8 * i + 2]; w += h[8 * i + 3]; tiles += h[8 * i + 4]; }
+        fprintf(stderr, "[tsasr prof] mode=%d ctas=%d tiles/cta=%.1f cycles/cta=%.0f wait: acc_empty=%.1f%% a_full=%.1f%% w_full=%.1f%% other=%.1f%%  cycles/tile=%.0f\n",
+                MODE, grid, tiles / grid, tot / grid, 100 * acc / tot, 100 * a / tot, 100 * w / tot, 100 * (tot - acc - a - w) / tot, tot / tiles);
+        delete[] h;
+        cudaFree(d_prof);
+    }
     return TSASR_OK;
 }
 
@@ -249,9 +283,9 @@ int tsasr_joint_fwd(const void* enc, const void* dec, const void* W, const float
         return rc;
     p.lat2 = reinterpret_cast<float2*>(lat2);
     p.logz = logz;
-    CUtensorMap tmap;
-    if (int rc = make_tmap_2d_bf16(&tmap, W, (uint64_t)V, (uint64_t)H, kWStageK, kTileN, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
-    return launch_joint<MODE_FWD>(tmap, p, sms, static_cast<cudaStream_t>(stream));
+    JointMaps maps;
+    if (int rc = make_joint_maps(&maps, p, enc, dec, W)) return rc;
+    return launch_joint<MODE_FWD>(maps, p, sms, static_cast<cudaStream_t>(stream));
 }
 
 int tsasr_joint_debug_logits(const void* enc, const void* dec, const void* W, const float* bias, int B, int T, int U,
@@ -280,9 +314,9 @@ int tsasr_joint_debug_logits(const void* enc, const void* dec, const void* W, co
     if (int rc = fill_joint_params(p, enc, dec, bias, nullptr, d_len, d_len + B, B, T, U, H, V, 0, act_kind, act_param, max_smem))
         return rc;
     p.dbg_logits = logits_out;
-    CUtensorMap tmap;
-    if (int rc = make_tmap_2d_bf16(&tmap, W, (uint64_t)V, (uint64_t)H, kWStageK, kTileN, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
-    return launch_joint<MODE_DEBUG>(tmap, p, sms, static_cast<cudaStream_t>(stream));
+    JointMaps maps;
+    if (int rc = make_joint_maps(&maps, p, enc, dec, W)) return rc;
+    return launch_joint<MODE_DEBUG>(maps, p, sms, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -6,20 +6,24 @@
 // Linear (SB/nnet/linear.py:74) and the log-softmax that follows (SB/nnet/losses.py:72-79,84) without
 // ever writing J ([B,T,U,H]) or the logits ([B,T,U,V]) to HBM.
 //
-// One persistent CTA per SM, 10 warps:
-//   warp 0      TMA producer: streams W k-slices [256 v x 32 h] (SWIZZLE_64B) through a 4+-stage ring
-//   warp 1      allocates TMEM, then ONE lane issues tcgen05.mma (M=128, N<=256, K=16, bf16 -> fp32)
-//   warps 2-5   A producers: build the 128-cell x H operand in shared memory in the canonical
-//               K-major SWIZZLE_128B layout (broadcast add + activation + bf16 round fused here);
-//               the operand stays resident for all N tiles of the cell tile
-//   warps 6-9   epilogue: tcgen05.ld the accumulator (double-buffered, 2 x 256 TMEM columns) and
-//               either run the online log-softmax keeping {lp_blank, lp_emit, logZ} (MODE_FWD), or
-//               recompute the softmax and emit bf16 dlogits tiles as pre-swizzled operand images
-//               for the backward GEMMs (MODE_GRAD), or dump raw logits (MODE_DEBUG, tests only).
+// One persistent CTA per SM, 20 warps (640 threads):
+//   warp 0       TMA producer: streams W k-slices [256 v x 32 h] (SWIZZLE_64B) through a 3-stage ring
+//   warp 1       allocates TMEM, then ONE lane issues tcgen05.mma (M=128, N<=256, K=16, bf16 -> fp32)
+//   warp 2       TMA producer: stages the enc [tT x 64] and dec [tU x 64] bf16 slices of the current
+//                k-block in a small shared-memory ring (so the A producers never wait on L2)
+//   warps 4-11   A producers: build the 128-cell x H operand in shared memory in the canonical
+//                K-major SWIZZLE_128B layout (broadcast add + activation + bf16 round fused here);
+//                the operand stays resident for all N tiles of the cell tile
+//   warps 12-19  epilogue, two groups of four warps; group g owns accumulator buffer g (2 x 256 TMEM
+//                columns), so vocabulary tiles alternate between the groups.  MODE_FWD: online
+//                log-softmax keeping {lp_blank, lp_emit, logZ} (the groups merge their running
+//                (max, sum) through shared memory at the end of a cell tile); MODE_GRAD: recompute the
+//                softmax and emit bf16 dlogits tiles as pre-swizzled operand images for the backward
+//                GEMMs; MODE_DEBUG: dump raw logits (tests only).
 //
 // A cell tile is tT consecutive frames x tU consecutive label positions of one utterance
-// (tT * tU = 128, row r = ui * tT + ti); tiles completely outside the utterance's T_b x U_b
-// rectangle are skipped by every role.
+// (tT * tU = 128, tT in {8,16,32}, row r = ui * tT + ti); tiles completely outside the utterance's
+// T_b x U_b rectangle are skipped by every role.
 #pragma once
 
 #include <cuda.h>
@@ -35,18 +39,19 @@ static constexpr int kABlockBytes = kTileM * kABlockK * 2;  // 16 KB
 static constexpr int kWStageK = 32;       // W stage: 32 bf16 = one 64-byte swizzle row
 static constexpr int kWStageBytes = kTileN * kWStageK * 2;  // 16 KB
 static constexpr int kMaxKB = 10;         // H <= 640
-static constexpr int kMaxWStages = 8;
-static constexpr int kNumThreads = 320;
-static constexpr int kNumProducerThreads = 128;
-static constexpr int kNumEpilogueThreads = 128;
+static constexpr int kMaxWStages = 3;
+static constexpr int kSliceRingBytes = 9216;  // enc/dec slice ring: 3 slots of 24 rows or 2 slots of 36 rows
+static constexpr int kNumThreads = 640;
+static constexpr int kNumProducerWarps = 8;
+static constexpr int kNumEpilogueWarps = 8;
+static constexpr int kFirstProducerWarp = 4;
+static constexpr int kFirstEpilogueWarp = 12;
 static constexpr float kLog2eF = 1.4426950408889634f;
 static constexpr float kLn2F = 0.6931471805599453f;
 
 enum JointMode : int { MODE_FWD = 0, MODE_GRAD = 1, MODE_DEBUG = 2 };
 
 struct JointParams {
-    const __nv_bfloat16* enc;   // [B,T,H]
-    const __nv_bfloat16* dec;   // [B,U,H]
     const float* bias;          // [V]
     const int* targets;         // [B,U-1]
     const int* logit_lengths;   // [B]
@@ -61,6 +66,7 @@ struct JointParams {
     int NT;                     // ceil(V / 256)
     int n_last;                 // UMMA N of the last vocabulary tile (multiple of 16)
     int num_w_stages;
+    int num_slice_slots;
     // MODE_FWD outputs (skewed lattice layout)
     float2* lat2;
     float* logz;
@@ -75,6 +81,7 @@ struct JointParams {
     __nv_bfloat16* J_img;       // [tile - tile_begin][KB][128 x 64] SWIZZLE_128B images
     // MODE_DEBUG output
     float* dbg_logits;          // [B,T,U,V]
+    long long* prof;            // development: per-CTA cycle counters of the MMA lane (or nullptr)
 };
 
 struct TileCoord { int b, t0, u0, Tb, Ub; bool live; };
@@ -97,49 +104,138 @@ __device__ __forceinline__ TileCoord tile_coord(const JointParams& p, int tile) 
 
 // shared memory carve-up (dynamic; base must be 1024-byte aligned)
 struct SmemLayout {
-    uint32_t a_off, w_off, bias_off, bar_off, tmem_off, total;
+    uint32_t a_off, w_off, slice_off, bias_off, xchg_off, bar_off, tmem_off, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int KB, int num_w_stages) {
     SmemLayout l;
     l.a_off = 0;
     l.w_off = l.a_off + (uint32_t)KB * kABlockBytes;
-    l.bias_off = l.w_off + (uint32_t)num_w_stages * kWStageBytes;
-    l.bar_off = l.bias_off + 2 * kTileN * 4;
-    // barriers: w_full[8] w_empty[8] a_full[10] a_empty[10] acc_full[2] acc_empty[2] = 40
+    l.slice_off = l.w_off + (uint32_t)num_w_stages * kWStageBytes;
+    l.bias_off = l.slice_off + kSliceRingBytes;
+    l.xchg_off = l.bias_off + 2 * kTileN * 4;
+    l.bar_off = l.xchg_off + 2 * kTileM * 16;
+    // barriers: w_full[3] w_empty[3] s_full[3] s_empty[3] a_full[10] a_empty[10] acc_full[2] acc_empty[2] = 36
     l.tmem_off = l.bar_off + 40 * 8;
     l.total = l.tmem_off + 16;
     return l;
 }
 
+// ---- activation, specialised at compile time inside the producer ----
+template <int ACT>
+__device__ __forceinline__ float act_t(float x, float param) {
+    if (ACT == ACT_LEAKY_RELU) return x >= 0.f ? x : x * param;
+    if (ACT == ACT_RELU) return fmaxf(x, 0.f);
+    if (ACT == ACT_TANH) return tanhf(x);
+    return x;
+}
+
+// A producers: J k-blocks from the staged enc/dec slices.
+template <int MODE, int ACT>
+__device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a, const uint8_t* slices,
+                                          uint64_t* s_full, uint64_t* s_empty, uint64_t* a_full, uint64_t* a_empty) {
+    const int lane = threadIdx.x & 31;
+    const int ptid = threadIdx.x - kFirstProducerWarp * 32;  // 0..255
+    const int c = ptid & 7;                                  // 16-byte chunk inside the 128-byte row
+    const int rg = ptid >> 3;                                // rows rg, rg+32, rg+64, rg+96
+    const int tT = 1 << p.tT_log2, tTm = tT - 1;
+    const int slot_bytes = (tT + (kTileM >> p.tT_log2)) * 128;
+    const int KB = p.KB, NSL = p.num_slice_slots;
+    uint32_t it = 0, slot = 0, sphase = 0;
+    int ti[4], ui[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = rg + 32 * i;
+        ti[i] = r & tTm;
+        ui[i] = r >> p.tT_log2;
+    }
+    for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(p, tile);
+        if (!tc.live) continue;
+        bool ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ok[i] = tc.t0 + ti[i] < tc.Tb && tc.u0 + ui[i] < tc.Ub;
+        for (int kb = 0; kb < KB; ++kb) {
+            // slices of this k-block: rows [0, tT) = enc frames, rows [tT, tT + tU) = dec label positions
+            mbar_wait(&s_full[slot], sphase, 0x580 | slot);
+            const uint8_t* sl = slices + slot * slot_bytes;
+            uint4 ev[4], dv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ev[i] = *reinterpret_cast<const uint4*>(sl + ti[i] * 128 + c * 16);
+                dv[i] = *reinterpret_cast<const uint4*>(sl + (tT + ui[i]) * 128 + c * 16);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[slot]);
+            if (++slot == (uint32_t)NSL) { slot = 0; sphase ^= 1; }
+
+            uint4 o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t* e = reinterpret_cast<const uint32_t*>(&ev[i]);
+                const uint32_t* d = reinterpret_cast<const uint32_t*>(&dv[i]);
+                uint32_t* op = reinterpret_cast<uint32_t*>(&o[i]);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const float lo = act_t<ACT>(bf16_lo(e[w]) + bf16_lo(d[w]), p.act_param);
+                    const float hi = act_t<ACT>(bf16_hi(e[w]) + bf16_hi(d[w]), p.act_param);
+                    op[w] = ok[i] ? pack_bf16x2(lo, hi) : 0u;
+                }
+            }
+            mbar_wait(&a_empty[kb], (it & 1) ^ 1, 0x500 | kb);
+            uint8_t* blk = smem_a + kb * kABlockBytes;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t off = sw128_offset((uint32_t)(rg + 32 * i), (uint32_t)c);
+                *reinterpret_cast<uint4*>(blk + off) = o[i];
+                if (MODE == MODE_GRAD) {
+                    uint8_t* img = reinterpret_cast<uint8_t*>(p.J_img) + ((size_t)(tile - p.tile_begin) * KB + kb) * kABlockBytes;
+                    *reinterpret_cast<uint4*>(img + off) = o[i];
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[kb]);
+        }
+        ++it;
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
-joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams p) {
+joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_enc,
+                  const __grid_constant__ CUtensorMap tmap_dec, const JointParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const SmemLayout L = smem_layout(p.KB, p.num_w_stages);
     uint8_t* smem_a = smem + L.a_off;
     uint8_t* smem_w = smem + L.w_off;
+    uint8_t* slices = smem + L.slice_off;
     float* bias_s = reinterpret_cast<float*>(smem + L.bias_off);
+    float4* xchg = reinterpret_cast<float4*>(smem + L.xchg_off);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* w_full = bars;
-    uint64_t* w_empty = bars + 8;
-    uint64_t* a_full = bars + 16;
-    uint64_t* a_empty = bars + 26;
-    uint64_t* acc_full = bars + 36;
-    uint64_t* acc_empty = bars + 38;
+    uint64_t* w_empty = bars + 3;
+    uint64_t* s_full = bars + 6;
+    uint64_t* s_empty = bars + 9;
+    uint64_t* a_full = bars + 12;
+    uint64_t* a_empty = bars + 22;
+    uint64_t* acc_full = bars + 32;
+    uint64_t* acc_empty = bars + 34;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int KB = p.KB, NT = p.NT, NS = p.num_w_stages;
+    const int KB = p.KB, NT = p.NT, NS = p.num_w_stages, NSL = p.num_slice_slots;
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B atoms need 1024-byte alignment
         for (int i = 0; i < NS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < KB; ++i) { mbar_init(&a_full[i], kNumProducerThreads / 32); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kNumEpilogueThreads / 32); }
+        for (int i = 0; i < NSL; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kNumProducerWarps); }
+        for (int i = 0; i < KB; ++i) { mbar_init(&a_full[i], kNumProducerWarps); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         fence_barrier_init();
     }
     if (warp_idx == 0 && lane == 0) tma_prefetch_desc(&tmap_w);
+    if (warp_idx == 2 && lane == 0) { tma_prefetch_desc(&tmap_enc); tma_prefetch_desc(&tmap_dec); }
     if (warp_idx == 1) tmem_alloc<512>(tmem_ptr);
     tcgen05_fence_before();
     __syncthreads();
@@ -164,110 +260,101 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
         }
     } else if (warp_idx == 1) {
         // ===================== MMA issuer =====================
+        // The single issuing lane is the serial resource of the kernel: everything that does not
+        // depend on the stage is hoisted, descriptors are advanced with 32-bit adds on their low word
+        // (start-address field, 16-byte units) and the loop body is wait -> 2 x MMA -> commit.
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, acc_it = 0, it = 0;
             const uint32_t idesc_full = make_idesc_bf16(kTileM, kTileN, 0, 0);
             const uint32_t idesc_last = make_idesc_bf16(kTileM, p.n_last, 0, 0);
+            // A: K-major SWIZZLE_128B, 8-row atoms 1024 B apart.  W: K-major SWIZZLE_64B, atoms 512 B apart.
+            const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smem_a), 0, 1024);
+            const uint64_t w_desc0 = (make_smem_desc_sw128(smem_u32(smem_w), 0, 512) & ~((uint64_t)7 << 61)) | ((uint64_t)4 << 61);
+            const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), w_hi = (uint32_t)(w_desc0 >> 32);
+            const uint32_t a_lo0 = (uint32_t)a_desc0, w_lo0 = (uint32_t)w_desc0;
+            long long t_acc = 0, t_a = 0, t_w = 0, t0 = 0;
+            const long long t_begin = clock64();
             for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x) {
                 if (!tile_coord(p, tile).live) continue;
                 for (int nt = 0; nt < NT; ++nt, ++acc_it) {
                     const uint32_t buf = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
+                    if (p.prof) t0 = clock64();
                     mbar_wait(&acc_empty[buf], acc_phase ^ 1, 0x200 | buf);
+                    if (p.prof) t_acc += clock64() - t0;
                     tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * kTileN;
                     const uint32_t idesc = nt == NT - 1 ? idesc_last : idesc_full;
-                    for (int kb = 0; kb < KB; ++kb) {
-                        if (nt == 0) {
+                    const bool first_nt = nt == 0, last_nt = nt == NT - 1;
+                    uint32_t a_lo = a_lo0;
+                    for (int kb = 0; kb < KB; ++kb, a_lo += kABlockBytes >> 4) {
+                        if (first_nt) {
+                            if (p.prof) t0 = clock64();
                             mbar_wait(&a_full[kb], it & 1, 0x300 | kb);
+                            if (p.prof) t_a += clock64() - t0;
                             tcgen05_fence_after();
                         }
-                        const uint32_t a_base = smem_u32(smem_a + kb * kABlockBytes);
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
+                            if (p.prof) t0 = clock64();
                             mbar_wait(&w_full[stage], phase, 0x400 | stage);
+                            if (p.prof) t_w += clock64() - t0;
                             tcgen05_fence_after();
-                            const uint32_t w_base = smem_u32(smem_w + stage * kWStageBytes);
-#pragma unroll
-                            for (int k = 0; k < 2; ++k) {
-                                // A: K-major SWIZZLE_128B, 8-row atoms 1024 B apart; K step = 32 B inside the row
-                                const uint64_t a_desc = make_smem_desc_sw128(a_base + (half * 2 + k) * 32, 0, 1024);
-                                // W: K-major SWIZZLE_64B, 8-row atoms 512 B apart
-                                uint64_t b_desc = make_smem_desc_sw128(w_base + k * 32, 0, 512);
-                                b_desc = (b_desc & ~((uint64_t)7 << 61)) | ((uint64_t)4 << 61);
-                                umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | half | k) != 0);
-                            }
+                            const uint32_t w_lo = w_lo0 + stage * (kWStageBytes >> 4);
+                            const uint32_t al = a_lo + half * 4;  // 64 bytes into the 128-byte row
+                            umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | al, ((uint64_t)w_hi << 32) | w_lo, idesc, (kb | half) != 0);
+                            umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | (al + 2), ((uint64_t)w_hi << 32) | (w_lo + 2), idesc, 1u);
                             umma_commit(&w_empty[stage]);
                             if (++stage == (uint32_t)NS) { stage = 0; phase ^= 1; }
                         }
-                        if (nt == NT - 1) umma_commit(&a_empty[kb]);
+                        if (last_nt) umma_commit(&a_empty[kb]);
                     }
                     umma_commit(&acc_full[buf]);
                 }
                 ++it;
             }
-        }
-    } else if (warp_idx < 6) {
-        // ===================== A producers: J = bf16(act(enc + dec)) =====================
-        const int ptid = threadIdx.x - 64;  // 0..127
-        const int c = ptid & 7;             // 16-byte chunk inside the 128-byte row
-        const int rg = ptid >> 3;           // rows rg, rg+16, ..., rg+112
-        const int tTm = (1 << p.tT_log2) - 1;
-        uint32_t it = 0;
-        for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x) {
-            const TileCoord tc = tile_coord(p, tile);
-            if (!tc.live) continue;
-            const __nv_bfloat16* enc_b = p.enc + (size_t)tc.b * p.T * p.H;
-            const __nv_bfloat16* dec_b = p.dec + (size_t)tc.b * p.U * p.H;
-            for (int kb = 0; kb < KB; ++kb) {
-                const int h0 = kb * kABlockK + c * 8;
-                uint4 ev[8], dv[8];
-                bool ok[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = rg + 16 * i;
-                    const int t = tc.t0 + (r & tTm), u = tc.u0 + (r >> p.tT_log2);
-                    ok[i] = t < tc.Tb && u < tc.Ub;
-                    const int tcl = min(t, p.T - 1), ucl = min(u, p.U - 1);
-                    ev[i] = __ldg(reinterpret_cast<const uint4*>(enc_b + (size_t)tcl * p.H + h0));
-                    dv[i] = __ldg(reinterpret_cast<const uint4*>(dec_b + (size_t)ucl * p.H + h0));
-                }
-                mbar_wait(&a_empty[kb], (it & 1) ^ 1, 0x500 | kb);
-                uint8_t* blk = smem_a + kb * kABlockBytes;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = rg + 16 * i;
-                    uint4 o;
-                    const uint32_t* e = reinterpret_cast<const uint32_t*>(&ev[i]);
-                    const uint32_t* d = reinterpret_cast<const uint32_t*>(&dv[i]);
-                    uint32_t* op = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        const float lo = act_apply(bf16_lo(e[w]) + bf16_lo(d[w]), p.act_kind, p.act_param);
-                        const float hi = act_apply(bf16_hi(e[w]) + bf16_hi(d[w]), p.act_kind, p.act_param);
-                        op[w] = ok[i] ? pack_bf16x2(lo, hi) : 0u;
-                    }
-                    const uint32_t off = sw128_offset((uint32_t)r, (uint32_t)c);
-                    *reinterpret_cast<uint4*>(blk + off) = o;
-                    if (MODE == MODE_GRAD) {
-                        uint8_t* img = reinterpret_cast<uint8_t*>(p.J_img) +
-                                       ((size_t)(tile - p.tile_begin) * KB + kb) * kABlockBytes;
-                        *reinterpret_cast<uint4*>(img + off) = o;
-                    }
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&a_full[kb]);
+            if (p.prof) {
+                long long* o = p.prof + blockIdx.x * 8;
+                o[0] = clock64() - t_begin; o[1] = t_acc; o[2] = t_a; o[3] = t_w; o[4] = it;
             }
-            ++it;
         }
-    } else {
+    } else if (warp_idx == 2) {
+        // ===================== enc / dec slice producer (TMA) =====================
+        if (lane == 0) {
+            const int tT = 1 << p.tT_log2, tU = kTileM >> p.tT_log2;
+            const int slot_bytes = (tT + tU) * 128;
+            uint32_t slot = 0, phase = 0;
+            for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x) {
+                const TileCoord tc = tile_coord(p, tile);
+                if (!tc.live) continue;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&s_empty[slot], phase ^ 1, 0x180 | slot);
+                    uint8_t* sl = slices + slot * slot_bytes;
+                    mbar_arrive_expect_tx(&s_full[slot], slot_bytes);
+                    tma_load_2d(sl, &tmap_enc, &s_full[slot], kb * kABlockK, tc.b * p.T + tc.t0);
+                    tma_load_2d(sl + tT * 128, &tmap_dec, &s_full[slot], kb * kABlockK, tc.b * p.U + tc.u0);
+                    if (++slot == (uint32_t)NSL) { slot = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx >= kFirstProducerWarp && warp_idx < kFirstEpilogueWarp) {
+        // ===================== A producers: J = bf16(act(enc + dec)) =====================
+        switch (p.act_kind) {
+            case ACT_LEAKY_RELU: produce_a<MODE, ACT_LEAKY_RELU>(p, smem_a, slices, s_full, s_empty, a_full, a_empty); break;
+            case ACT_RELU: produce_a<MODE, ACT_RELU>(p, smem_a, slices, s_full, s_empty, a_full, a_empty); break;
+            case ACT_TANH: produce_a<MODE, ACT_TANH>(p, smem_a, slices, s_full, s_empty, a_full, a_empty); break;
+            default: produce_a<MODE, ACT_IDENTITY>(p, smem_a, slices, s_full, s_empty, a_full, a_empty); break;
+        }
+    } else if (warp_idx >= kFirstEpilogueWarp) {
         // ===================== epilogue =====================
-        const int q = warp_idx & 3;             // TMEM lane quarter owned by this warp
-        const int row = q * 32 + lane;          // tile row == TMEM lane
-        const int etid = threadIdx.x - 192;     // 0..127 (bias staging index)
+        const int grp = (warp_idx - kFirstEpilogueWarp) >> 2;  // accumulator buffer owned by this group
+        const int q = warp_idx & 3;                            // TMEM lane quarter owned by this warp
+        const int row = q * 32 + lane;                         // tile row == TMEM lane
+        const int gtid = (threadIdx.x - kFirstEpilogueWarp * 32) & 127;  // 0..127 inside the group
         const int tTm = (1 << p.tT_log2) - 1;
         const int n_lab = max(1, 32 >> p.tT_log2);  // distinct label positions inside one warp
-        uint32_t acc_it = 0;
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + grp * kTileN;
+        float* bias_g = bias_s + grp * kTileN;
+        uint32_t acc_it = 0, it = 0;
         for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x) {
             const TileCoord tc = tile_coord(p, tile);
             if (!tc.live) continue;
@@ -278,8 +365,8 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
             const size_t cell_o = valid ? skew_index(tc.b, t, u, p.T, p.U) : 0;
 
             // per-row state
-            float run_m = -INFINITY, run_s = 0.f, y_blank = 0.f, y_label = 0.f;  // MODE_FWD (log2 domain)
-            float nz2 = 0.f, occ = 0.f, ob = 0.f, oe = 0.f, p_blank = 0.f, p_label = 0.f;  // MODE_GRAD
+            float run_m = -INFINITY, run_s = 0.f, y_blank = -INFINITY, y_label = -INFINITY;  // MODE_FWD (log2 domain)
+            float nz2 = 0.f, occ = 0.f, ob = 0.f, oe = 0.f, p_blank = 0.f, p_label = 0.f;    // MODE_GRAD
             if (MODE == MODE_GRAD && valid) {
                 const float Lp = -p.cost[tc.b];
                 const float dy = p.dcost ? p.dcost[tc.b] : 1.f;
@@ -297,26 +384,28 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
             }
 
             for (int nt = 0; nt < NT; ++nt, ++acc_it) {
-                const uint32_t buf = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
-                // stage bias * log2(e) for this vocabulary tile (double-buffered with the accumulator)
+                if ((int)(acc_it & 1) != grp) continue;  // the other group owns this accumulator buffer
+                const uint32_t acc_phase = (acc_it >> 1) & 1;
+                // stage bias * log2(e) for this vocabulary tile (one buffer per group)
                 {
-                    const int v0 = nt * kTileN + etid, v1 = v0 + 128;
-                    bias_s[buf * kTileN + etid] = v0 < p.V ? p.bias[v0] * kLog2eF : 0.f;
-                    bias_s[buf * kTileN + etid + 128] = v1 < p.V ? p.bias[v1] * kLog2eF : 0.f;
-                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    const int v0 = nt * kTileN + gtid, v1 = v0 + 128;
+                    asm volatile("bar.sync %0, 128;" ::"r"(4 + grp) : "memory");  // previous tile's reads are done
+                    bias_g[gtid] = v0 < p.V ? p.bias[v0] * kLog2eF : 0.f;
+                    bias_g[gtid + 128] = v1 < p.V ? p.bias[v1] * kLog2eF : 0.f;
+                    asm volatile("bar.sync %0, 128;" ::"r"(4 + grp) : "memory");
                 }
-                mbar_wait(&acc_full[buf], acc_phase, 0x600 | buf);
+                mbar_wait(&acc_full[grp], acc_phase, 0x600 | grp);
                 tcgen05_fence_after();
                 const int n_cols = nt == NT - 1 ? p.n_last : kTileN;
-                for (int cc = 0; cc < n_cols; cc += 32) {
-                    uint32_t raw[32];
-                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kTileN + cc, raw);
+                for (int cc = 0; cc < n_cols; cc += 16) {
+                    uint32_t raw[16];
+                    tmem_ld_32x32b_x16(tmem_row + cc, raw);
                     tmem_ld_wait();
                     const int col0 = nt * kTileN + cc;
-                    float y[32];  // logits * log2(e)
-                    const float4* b4 = reinterpret_cast<const float4*>(bias_s + buf * kTileN + cc);
+                    float y[16];  // logits * log2(e)
+                    const float4* b4 = reinterpret_cast<const float4*>(bias_g + cc);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                         const float4 bb = b4[j];
                         y[4 * j + 0] = fmaf(__uint_as_float(raw[4 * j + 0]), kLog2eF, bb.x);
                         y[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), kLog2eF, bb.y);
@@ -324,34 +413,43 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                         y[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), kLog2eF, bb.w);
                     }
                     if (MODE == MODE_FWD) {
-                        if (col0 + 32 > p.V) {
+                        if (col0 + 16 > p.V) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
+                            for (int j = 0; j < 16; ++j)
                                 if (col0 + j >= p.V) y[j] = -INFINITY;
                         }
-                        float cm = y[0];
+                        // pairwise trees keep the dependency chains short
+                        float m8[8], m4[4];
 #pragma unroll
-                        for (int j = 1; j < 32; ++j) cm = fmaxf(cm, y[j]);
+                        for (int j = 0; j < 8; ++j) m8[j] = fmaxf(y[2 * j], y[2 * j + 1]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) m4[j] = fmaxf(m8[2 * j], m8[2 * j + 1]);
+                        const float cm = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
                         const float mn = fmaxf(run_m, cm);
-                        float acc = run_s * exp2f(run_m - mn);
+                        float e[16];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc += exp2f(y[j] - mn);
-                        run_s = acc;
+                        for (int j = 0; j < 16; ++j) e[j] = ex2_approx(y[j] - mn);
+                        float s8[8], s4[4];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) s8[j] = e[2 * j] + e[2 * j + 1];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) s4[j] = s8[2 * j] + s8[2 * j + 1];
+                        run_s = run_s * ex2_approx(run_m - mn) + ((s4[0] + s4[1]) + (s4[2] + s4[3]));
                         run_m = mn;
                         // blank / label logits: the index is warp-uniform per label position
-                        if (p.blank >= col0 && p.blank < col0 + 32) {
+                        if (p.blank >= col0 && p.blank < col0 + 16) {
                             const int idx = p.blank - col0;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
+                            for (int j = 0; j < 16; ++j)
                                 if (j == idx) y_blank = y[j];
                         }
                         for (int k = 0; k < n_lab; ++k) {
                             const int lab_k = __shfl_sync(0xffffffffu, label, (k << p.tT_log2) & 31);
-                            if (lab_k >= col0 && lab_k < col0 + 32) {
+                            if (lab_k >= col0 && lab_k < col0 + 16) {
                                 const int idx = lab_k - col0;
                                 float sel = 0.f;
 #pragma unroll
-                                for (int j = 0; j < 32; ++j)
+                                for (int j = 0; j < 16; ++j)
                                     if (j == idx) sel = y[j];
                                 if ((lane >> p.tT_log2) == k || n_lab == 1) y_label = sel;
                             }
@@ -359,32 +457,32 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                     } else if (MODE == MODE_GRAD) {
                         // dlogits = occ * softmax - [blank] ob - [label] oe, emitted as bf16 into the
                         // [128 x 64] SWIZZLE_128B image of this (tile, 64-column block)
-                        uint32_t packed[16];
+                        uint32_t packed[8];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float g0 = col0 + 2 * j < p.V ? occ * exp2f(y[2 * j] + nz2) : 0.f;
-                            float g1 = col0 + 2 * j + 1 < p.V ? occ * exp2f(y[2 * j + 1] + nz2) : 0.f;
+                        for (int j = 0; j < 8; ++j) {
+                            const float g0 = col0 + 2 * j < p.V ? occ * ex2_approx(y[2 * j] + nz2) : 0.f;
+                            const float g1 = col0 + 2 * j + 1 < p.V ? occ * ex2_approx(y[2 * j + 1] + nz2) : 0.f;
                             packed[j] = pack_bf16x2(g0, g1);
                         }
                         const int vb = col0 >> 6;             // 64-column block index
-                        const int chunk0 = (col0 & 63) >> 3;  // 0 or 4
+                        const int chunk0 = (col0 & 63) >> 3;  // 0, 2, 4 or 6
                         uint8_t* img = reinterpret_cast<uint8_t*>(p.dY_img) +
                                        ((size_t)(tile - p.tile_begin) * (NT * 4) + vb) * kABlockBytes;
 #pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4) {
-                            uint4 o = make_uint4(packed[4 * c4], packed[4 * c4 + 1], packed[4 * c4 + 2], packed[4 * c4 + 3]);
-                            *reinterpret_cast<uint4*>(img + sw128_offset((uint32_t)row, (uint32_t)(chunk0 + c4))) = o;
+                        for (int c2 = 0; c2 < 2; ++c2) {
+                            const uint4 o = make_uint4(packed[4 * c2], packed[4 * c2 + 1], packed[4 * c2 + 2], packed[4 * c2 + 3]);
+                            *reinterpret_cast<uint4*>(img + sw128_offset((uint32_t)row, (uint32_t)(chunk0 + c2))) = o;
                         }
                         // patch the two special columns from the saved lattice (same thread, program order)
                         if (valid) {
                             __nv_bfloat16* rowp = reinterpret_cast<__nv_bfloat16*>(img);
-                            if (p.blank >= col0 && p.blank < col0 + 32) {
+                            if (p.blank >= col0 && p.blank < col0 + 16) {
                                 float g = occ * p_blank - ob;
                                 if (label == p.blank) g -= oe;
                                 const int cv = p.blank & 63;
                                 rowp[(sw128_offset((uint32_t)row, (uint32_t)(cv >> 3)) >> 1) + (cv & 7)] = __float2bfloat16_rn(g);
                             }
-                            if (label >= col0 && label < col0 + 32 && label != p.blank) {
+                            if (label >= col0 && label < col0 + 16 && label != p.blank) {
                                 const int cv = label & 63;
                                 rowp[(sw128_offset((uint32_t)row, (uint32_t)(cv >> 3)) >> 1) + (cv & 7)] =
                                     __float2bfloat16_rn(occ * p_label - oe);
@@ -394,37 +492,48 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                         if (valid) {
                             float* out = p.dbg_logits + (((size_t)tc.b * p.T + t) * p.U + u) * p.V;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
+                            for (int j = 0; j < 16; ++j)
                                 if (col0 + j < p.V) out[col0 + j] = y[j] * kLn2F;
                         }
                     }
                 }
                 if (MODE == MODE_GRAD && n_cols < kTileN) {
-                    // zero-fill the 32-column chunks of the last tile the MMA did not produce, so the
+                    // zero-fill the 16-column chunks of the last tile the MMA did not produce, so the
                     // backward GEMMs read finite zeros for the padded vocabulary columns
                     const int cols_pad = ((p.V + 63) / 64) * 64 - nt * kTileN;  // columns the images cover
-                    for (int cc = ((n_cols + 31) / 32) * 32; cc < cols_pad; cc += 32) {
+                    for (int cc = n_cols; cc < cols_pad; cc += 16) {
                         const int col0 = nt * kTileN + cc;
                         uint8_t* img = reinterpret_cast<uint8_t*>(p.dY_img) +
                                        ((size_t)(tile - p.tile_begin) * (NT * 4) + (col0 >> 6)) * kABlockBytes;
                         const int chunk0 = (col0 & 63) >> 3;
 #pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4)
-                            *reinterpret_cast<uint4*>(img + sw128_offset((uint32_t)row, (uint32_t)(chunk0 + c4))) =
+                        for (int c2 = 0; c2 < 2; ++c2)
+                            *reinterpret_cast<uint4*>(img + sw128_offset((uint32_t)row, (uint32_t)(chunk0 + c2))) =
                                 make_uint4(0, 0, 0, 0);
                     }
                 }
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                if (lane == 0) mbar_arrive(&acc_empty[grp]);
             }
-            if (MODE == MODE_FWD && valid) {
-                const float lz2 = run_m + log2f(run_s);
-                const float lpb = (y_blank - lz2) * kLn2F;
-                const float lpe = label >= 0 ? (y_label - lz2) * kLn2F : -INFINITY;
-                p.lat2[cell_o] = make_float2(lpb, lpe);
-                p.logz[cell_o] = lz2 * kLn2F;
+            if (MODE == MODE_FWD) {
+                // merge the two groups' running (max, sum) and picked logits; group 0 writes the lattice
+                float4* xb = xchg + (it & 1) * kTileM;
+                if (grp == 1) xb[row] = make_float4(run_m, run_s, y_blank, y_label);
+                asm volatile("bar.sync 3, 256;" ::: "memory");
+                if (grp == 0 && valid) {
+                    const float4 o = xb[row];
+                    const float mn = fmaxf(run_m, o.x);
+                    const float s = run_s * ex2_approx(run_m - mn) + o.y * ex2_approx(o.x - mn);
+                    const float lz2 = mn + lg2_approx(s);
+                    const float yb = fmaxf(y_blank, o.z), yl = fmaxf(y_label, o.w);
+                    const float lpb = (yb - lz2) * kLn2F;
+                    const float lpe = label >= 0 ? (yl - lz2) * kLn2F : -INFINITY;
+                    p.lat2[cell_o] = make_float2(lpb, lpe);
+                    p.logz[cell_o] = lz2 * kLn2F;
+                }
             }
+            ++it;
         }
     }
 
