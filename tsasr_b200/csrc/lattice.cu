@@ -153,71 +153,95 @@ logits_to_lattice_kernel(const T* __restrict__ logits, const int* __restrict__ t
 // one named barrier per step.  Lattice rows are prefetched PF diagonals ahead (they do not depend
 // on the DP state), so the per-step critical path is shuffle + logaddexp only.
 // ------------------------------------------------------------------------------------------------
-static constexpr int kDpPrefetch = 4;
+static constexpr int kDpPrefetch = 16;      // diagonals in flight per column (cp.async ring in shared memory)
+static constexpr float kDpNeg = -1.0e30f;  // "log 0" sentinel: finite, so no -inf special cases on the chain
 
+// log2(2^a + 2^b): the whole per-step dependency chain is FADD -> MUFU.EX2 -> FADD -> MUFU.LG2 -> FADD
+__device__ __forceinline__ float logaddexp2_fast(float a, float b) {
+    return fmaxf(a, b) + lg2_approx(1.f + ex2_approx(-fabsf(a - b)));
+}
+
+// One in-order warp per 32 columns walks ~T+U dependent steps, so the per-step critical path is all that
+// matters.  Lattice values are staged by per-thread cp.async into a shared-memory ring kDpPrefetch
+// diagonals ahead (cp.async groups retire in order, so `wait_group kDpPrefetch-1` waits for exactly the
+// oldest one; register prefetch cannot do that: scoreboard slots are shared between the loads in flight),
+// loop invariants are pinned in registers, and the boundary cases are folded into the initial values.
 template <bool BETA>
 __device__ __forceinline__ void dp_pass(const float2* __restrict__ lat, float* __restrict__ out, int Tb, int Ub,
-                                        int U, float* __restrict__ result, float* xchg /* [2][32] */) {
-    const int j = threadIdx.x;
+                                        int U, float* __restrict__ result, float* xchg /* [2][32] */, float2* ring) {
+    int j;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(j));
     const int lane = j & 31, warp = j >> 5;
     const int nwarps = (Ub + 31) >> 5;
     if (warp >= nwarps) return;
     const int nthreads_active = nwarps << 5;
-    const int u = BETA ? (Ub - 1 - j) : j;  // may be negative for idle lanes of the last warp
     const bool col_ok = j < Ub;
+    const unsigned Tb_eff = col_ok ? (unsigned)Tb : 0u;  // (unsigned)tl < Tb_eff  <=>  column active at tl
+    const int u = col_ok ? (BETA ? (Ub - 1 - j) : j) : 0;
     const int S = Tb + Ub - 1;
+    const long long stride = BETA ? -(long long)U : (long long)U;
+    const float2* lp = lat + (BETA ? (long long)(S - 1) * U : 0ll) + u;
+    float* op = out + (BETA ? (long long)(S - 1) * U : 0ll) + u;
+    // shared exchange slots: warp w writes slot [parity][w], warp w+1 reads it one step later
+    uint32_t x_wr = smem_u32(xchg) + warp * 4, x_rd = x_wr - 4;
+    uint32_t r_base = smem_u32(ring) + j * 8;           // this column's ring: slot k at r_base + k * slot_stride
+    const uint32_t slot_stride = blockDim.x * 8;
+    asm volatile("" : "+r"(x_rd), "+r"(x_wr), "+r"(r_base));
+    const bool rd_lds = lane == 0 && warp > 0;
+    const bool wr_sts = lane == 31;
+    const bool multi = nwarps > 1;
 
-    auto row_of = [&](int s) { return BETA ? (S - 1 - s) : s; };
-    auto fetch = [&](int s) -> float2 {
-        const int tl = s - j;
-        if (col_ok && tl >= 0 && tl < Tb) return lat[(size_t)row_of(s) * U + u];
-        return make_float2(0.f, 0.f);
-    };
-
-    float2 buf[kDpPrefetch];
+    int tl = -j;  // local time of this column at step s
 #pragma unroll
-    for (int k = 0; k < kDpPrefetch; ++k) buf[k] = fetch(k);
+    for (int k = 0; k < kDpPrefetch; ++k) {
+        if ((unsigned)(tl + k) < Tb_eff)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(r_base + k * slot_stride), "l"(lp) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        lp += stride;
+    }
 
-    float carry = -INFINITY;  // alpha: a(t-1,u)+blank(t-1,u)   beta: b(t+1,u)
-    float pass = -INFINITY;   // alpha: a(t,u)+emit(t,u)        beta: b(t,u)      (handed to thread j+1)
+    // alpha: carry = a(t-1,u)+blank(t-1,u), pass = a(t,u)+emit(t,u); beta: carry = pass = b(t,u) (log2 units).
+    // Column 0 starts from carry = 0 so the generic update yields a(0,0) = 0 / b(T-1,U-1) = lp_blank.
+    float carry = j == 0 ? 0.f : kDpNeg;
+    float pass = kDpNeg;
+    float res = 0.f;
 
     for (int s0 = 0; s0 < S; s0 += kDpPrefetch) {
 #pragma unroll
         for (int k = 0; k < kDpPrefetch; ++k) {
-            const int s = s0 + k;
-            if (s < S) {  // block-uniform
-                const float2 cell = buf[k];
-                buf[k] = fetch(s + kDpPrefetch);
+            if (s0 + k < S) {  // block-uniform
+                asm volatile("cp.async.wait_group %0;" ::"n"(kDpPrefetch - 1) : "memory");
+                float2 raw;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(raw.x), "=f"(raw.y) : "r"(r_base + k * slot_stride));
+                if ((unsigned)(tl + kDpPrefetch) < Tb_eff)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(r_base + k * slot_stride), "l"(lp) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                lp += stride;
+                const float2 cell = make_float2(raw.x * kLog2e, raw.y * kLog2e);
                 float from_left = __shfl_up_sync(0xffffffffu, pass, 1);
-                if (lane == 0) from_left = warp == 0 ? -INFINITY : xchg[((s + 1) & 1) * 32 + warp - 1];
-                const int tl = s - j;
-                if (col_ok && tl >= 0 && tl < Tb) {
-                    float val;
-                    if (BETA) {
-                        if (tl == 0 && j == 0) val = cell.x;  // b(T-1,U-1) = lp_blank
-                        else {
-                            const float stay = carry + cell.x;
-                            const float emit = j == 0 ? -INFINITY : from_left + cell.y;
-                            val = logaddexp_fast(stay, emit);
-                        }
-                        carry = val;
-                        pass = val;
-                    } else {
-                        if (tl == 0 && j == 0) val = 0.f;  // a(0,0) = 0
-                        else val = logaddexp_fast(carry, j == 0 ? -INFINITY : from_left);
-                        carry = val + cell.x;
-                        pass = val + cell.y;
-                    }
-                    out[(size_t)row_of(s) * U + u] = val;
-                    if (tl == Tb - 1 && j == Ub - 1) *result = BETA ? val : carry;  // log P(y|x)
+                if (lane == 0) from_left = kDpNeg;
+                if (rd_lds) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(from_left) : "r"(x_rd + ((k + 1) & 1) * 128));
+                const bool active = (unsigned)tl < Tb_eff;
+                float val;
+                if (BETA) {
+                    val = logaddexp2_fast(carry + cell.x, from_left + cell.y);
+                    if (active) { carry = val; pass = val; res = val; }
+                } else {
+                    val = logaddexp2_fast(carry, from_left);
+                    if (active) { carry = val + cell.x; pass = val + cell.y; res = carry; }
                 }
-                if (nwarps > 1) {
-                    if (lane == 31) xchg[(s & 1) * 32 + warp] = pass;
+                if (active) *op = val * kLn2;
+                op += stride;
+                ++tl;
+                if (multi) {
+                    if (wr_sts) asm volatile("st.shared.f32 [%0], %1;" ::"r"(x_wr + (k & 1) * 128), "f"(pass) : "memory");
                     asm volatile("bar.sync 1, %0;" ::"r"(nthreads_active) : "memory");
                 }
             }
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (j == Ub - 1) *result = res * kLn2;  // log P(y|x): last active step of the last column
 }
 
 __global__ void __launch_bounds__(1024)
@@ -225,12 +249,13 @@ alpha_beta_kernel(const float2* __restrict__ lat2, const int* __restrict__ logit
                   const int* __restrict__ target_lengths, int Tmax, int U, float* __restrict__ alpha,
                   float* __restrict__ beta, float* __restrict__ ll_alpha, float* __restrict__ ll_beta) {
     __shared__ float xchg[64];
+    extern __shared__ __align__(16) float2 dp_ring[];  // [kDpPrefetch][blockDim.x]
     const int b = blockIdx.x;
     const int Tb = logit_lengths[b], Ub = target_lengths[b] + 1;
     const size_t base = (size_t)b * (size_t)(Tmax + U - 1) * (size_t)U;
     // Each utterance's own rectangle starts at diagonal 0 of its slab: cell (t,u) -> row t+u.
-    if (blockIdx.y == 0) dp_pass<false>(lat2 + base, alpha + base, Tb, Ub, U, ll_alpha + b, xchg);
-    else dp_pass<true>(lat2 + base, beta + base, Tb, Ub, U, ll_beta + b, xchg);
+    if (blockIdx.y == 0) dp_pass<false>(lat2 + base, alpha + base, Tb, Ub, U, ll_alpha + b, xchg, dp_ring);
+    else dp_pass<true>(lat2 + base, beta + base, Tb, Ub, U, ll_beta + b, xchg, dp_ring);
 }
 
 // cost[b] = -log P from the beta pass (torchaudio: costs = -beta(0,0)); written by a tiny kernel so the
@@ -381,7 +406,13 @@ cudaError_t launch_logits_to_lattice(const void* logits, int dtype, const int* t
 cudaError_t launch_alpha_beta(const float2* lat2, const int* ll, const int* tl, int B, int Tmax, int U, float* alpha,
                               float* beta, float* ll_alpha, float* ll_beta, float* cost, cudaStream_t st) {
     const int threads = ((U + 31) / 32) * 32;
-    alpha_beta_kernel<<<dim3(B, 2), threads, 0, st>>>(lat2, ll, tl, Tmax, U, alpha, beta, ll_alpha, ll_beta);
+    const size_t ring_bytes = (size_t)kDpPrefetch * threads * sizeof(float2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDpPrefetch * 1024 * (int)sizeof(float2));
+        attr_set = true;
+    }
+    alpha_beta_kernel<<<dim3(B, 2), threads, ring_bytes, st>>>(lat2, ll, tl, Tmax, U, alpha, beta, ll_alpha, ll_beta);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     finalize_cost_kernel<<<(B + 127) / 128, 128, 0, st>>>(ll_beta, cost, B);
