@@ -124,6 +124,12 @@ static void choose_tile(int T, int U, int* tT_log2) {
     *tT_log2 = best_l;
 }
 
+// CTA pairs (cta_group::2) are the default; TSASR_DEBUG_NO_PAIR=1 selects the single-CTA kernel (A/B runs).
+static bool use_pair() {
+    static const bool v = getenv("TSASR_DEBUG_NO_PAIR") == nullptr;
+    return v;
+}
+
 static int fill_joint_params(JointParams& p, const void* enc, const void* dec, const float* bias,
                              const int32_t* targets, const int32_t* ll, const int32_t* tl, int B, int T, int U, int H,
                              int V, int blank, int act_kind, float act_param, int max_smem) {
@@ -148,7 +154,9 @@ static int fill_joint_params(JointParams& p, const void* enc, const void* dec, c
     p.tile_end = B * p.nTt * p.nTu;
     p.KB = H / 64;
     p.NT = (V + kTileN - 1) / kTileN;
-    p.n_last = ((V - (p.NT - 1) * kTileN) + 15) / 16 * 16;
+    // UMMA N of the last vocabulary tile: a multiple of 16 per CTA (pairs split N between the two CTAs)
+    const int n_gran = use_pair() ? 32 : 16;
+    p.n_last = ((V - (p.NT - 1) * kTileN) + n_gran - 1) / n_gran * n_gran;
     int ns = kMaxWStages;
     if (const char* env = getenv("TSASR_DEBUG_W_STAGES")) {  // development knob (pipeline-depth experiments)
         const int v = atoi(env);
@@ -167,19 +175,30 @@ struct JointMaps { CUtensorMap w, enc, dec; };
 // W [V,H]: 64-byte swizzled k-slices of 256 rows; enc [B*T,H] / dec [B*U,H]: plain [rows x 64] slices
 static int make_joint_maps(JointMaps* m, const JointParams& p, const void* enc, const void* dec, const void* W) {
     const int tT = 1 << p.tT_log2, tU = 128 >> p.tT_log2;
-    if (int rc = make_tmap_2d_bf16(&m->w, W, (uint64_t)p.V, (uint64_t)p.H, kWStageK, kTileN, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    if (use_pair()) {
+        if (int rc = make_tmap_2d_bf16(&m->w, W, (uint64_t)p.V, (uint64_t)p.H, kWStageKPair, kTileN / 2, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    } else {
+        if (int rc = make_tmap_2d_bf16(&m->w, W, (uint64_t)p.V, (uint64_t)p.H, kWStageK, kTileN, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    }
     if (int rc = make_tmap_2d_bf16(&m->enc, enc, (uint64_t)p.B * p.T, (uint64_t)p.H, kABlockK, tT, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
     if (int rc = make_tmap_2d_bf16(&m->dec, dec, (uint64_t)p.B * p.U, (uint64_t)p.H, kABlockK, tU, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
     return TSASR_OK;
 }
 
-template <int MODE>
-static int launch_joint(const JointMaps& maps, const JointParams& p, int num_sms, cudaStream_t st) {
+template <int MODE, bool PAIR>
+static int launch_joint_impl(const JointMaps& maps, const JointParams& p, int num_sms, cudaStream_t st) {
     const SmemLayout L = smem_layout(p.KB, p.num_w_stages);
-    cudaError_t e = cudaFuncSetAttribute(joint_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    auto kern = joint_gemm_kernel<MODE, PAIR>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(joint_gemm_kernel)");
     const int tiles = p.tile_end - p.tile_begin;
-    const int grid = tiles < num_sms ? tiles : num_sms;
+    int grid;
+    if (PAIR) {
+        const int pairs = (tiles + 1) / 2, max_pairs = num_sms / 2;
+        grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+    } else {
+        grid = tiles < num_sms ? tiles : num_sms;
+    }
     if (grid <= 0) return TSASR_OK;
     static const bool prof_on = getenv("TSASR_DEBUG_PROF") != nullptr;  // development: MMA-lane wait breakdown
     JointParams pp = p;
@@ -189,22 +208,44 @@ static int launch_joint(const JointMaps& maps, const JointParams& p, int num_sms
         cudaMemset(d_prof, 0, sizeof(long long) * 8 * grid);
         pp.prof = d_prof;
     }
-    joint_gemm_kernel<MODE><<<grid, kNumThreads, L.total, st>>>(maps.w, maps.enc, maps.dec, pp);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = L.total;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, maps.w, maps.enc, maps.dec, pp);
     ++g_launches;
+    if (e != cudaSuccess) return cuda_fail(e, "joint_gemm_kernel launch");
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "joint_gemm_kernel launch");
     if (prof_on) {
         cudaStreamSynchronize(st);
         long long* h = new long long[8 * grid];
         cudaMemcpy(h, d_prof, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
-        double tot = 0, acc = 0, a = 0, w = 0, tiles = 0;
-        for (int i = 0; i < grid; ++i) { tot += h[8 * i]; acc += h[8 * i + 1]; a += h[8 * i + 2]; w += h[8 * i + 3]; tiles += h[8 * i + 4]; }
-        fprintf(stderr, "[tsasr prof] mode=%d ctas=%d tiles/cta=%.1f cycles/cta=%.0f wait: acc_empty=%.1f%% a_full=%.1f%% w_full=%.1f%% other=%.1f%%  cycles/tile=%.0f\n",
-                MODE, grid, tiles / grid, tot / grid, 100 * acc / tot, 100 * a / tot, 100 * w / tot, 100 * (tot - acc - a - w) / tot, tot / tiles);
+        double tot = 0, acc = 0, a = 0, w = 0, rounds = 0, lsum = 0, lcnt = 0, tcom = 0;
+        int n = 0;
+        for (int i = 0; i < grid; ++i)
+            if (h[8 * i] > 0) { tot += h[8 * i]; acc += h[8 * i + 1]; a += h[8 * i + 2]; w += h[8 * i + 3]; rounds += h[8 * i + 4]; lsum += h[8 * i + 5]; lcnt += h[8 * i + 6]; tcom += h[8 * i + 7]; ++n; }
+        if (lcnt > 0) fprintf(stderr, "[tsasr prof] MMA issue blocks: %.0f stages per cta, %.0f cycles to issue the 4 MMAs of a stage, %.0f cycles in commits per stage\n", lcnt / n, lsum / lcnt, tcom / lcnt);
+        fprintf(stderr, "[tsasr prof] mode=%d pair=%d issuing ctas=%d rounds/cta=%.1f cycles/cta=%.0f wait: acc_empty=%.1f%% a_full=%.1f%% w_full=%.1f%% other=%.1f%%  cycles/round=%.0f\n",
+                MODE, (int)PAIR, n, rounds / n, tot / n, 100 * acc / tot, 100 * a / tot, 100 * w / tot, 100 * (tot - acc - a - w) / tot, tot / rounds);
         delete[] h;
         cudaFree(d_prof);
     }
     return TSASR_OK;
+}
+
+template <int MODE>
+static int launch_joint(const JointMaps& maps, const JointParams& p, int num_sms, cudaStream_t st) {
+    return use_pair() ? launch_joint_impl<MODE, true>(maps, p, num_sms, st) : launch_joint_impl<MODE, false>(maps, p, num_sms, st);
 }
 
 extern "C" {
