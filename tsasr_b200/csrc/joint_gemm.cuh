@@ -297,7 +297,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         for (int i = 0; i < NS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         for (int i = 0; i < NSL; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kNumProducerWarps); }
         for (int i = 0; i < KB; ++i) { mbar_init(&a_full[i], kNumProducerWarps * kCtas); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * kCtas); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kNumEpilogueWarps * kCtas); }
         fence_barrier_init();
     }
     if (warp_idx == kWarpTmaW && lane == 0) tma_prefetch_desc(&tmap_w);
@@ -460,30 +460,31 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         }
     } else if (warp_idx < kFirstEpilogueWarp + kNumEpilogueWarps) {
         // ===================== epilogue =====================
-        const int grp = (warp_idx - kFirstEpilogueWarp) >> 2;  // accumulator buffer owned by this group
+        const int grp = (warp_idx - kFirstEpilogueWarp) >> 2;  // column half of every vocabulary tile owned by this group
         const int q = warp_idx & 3;                            // TMEM lane quarter owned by this warp
         const int row = q * 32 + lane;                         // tile row == TMEM lane
         const int gtid = (threadIdx.x - kFirstEpilogueWarp * 32) & 127;  // 0..127 inside the group
         const int tTm = (1 << p.tT_log2) - 1;
         const int n_lab = max(1, 32 >> p.tT_log2);  // distinct label positions inside one warp
-        const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + grp * kTileN;
-        float* bias_g = bias_s + grp * kTileN;
+        const uint32_t tmem_row0 = tmem_base + ((uint32_t)(q * 32) << 16);
+        float* bias_g = bias_s + grp * kTileN;  // this group's 128 staged bias values (second half of the slot unused)
+        constexpr int kGrpCols = kTileN / 2;
         uint32_t acc_it = 0, it = 0;
-        float nb0 = 0.f, nb1 = 0.f;  // prefetched bias values of this group's next vocabulary tile
+        float nb0 = 0.f;  // prefetched bias value of the next vocabulary tile
         int nb_nt = -1;
-        const uint32_t acc_empty_leader = PAIR ? mapa_u32(smem_u32(&acc_empty[grp]), 0) : 0u;
+        const uint32_t acc_empty_leader0 = PAIR ? mapa_u32(smem_u32(&acc_empty[0]), 0) : 0u;
         for (int t0 = rounds.first; t0 < p.tile_end; t0 += rounds.step) {
             int tile;
             TileCoord tc;
             if (!rounds.open(p, t0, tile, tc)) continue;
             if (!tc.live) {  // dummy round: release the accumulators the pair's MMA stream wrote for us
                 for (int nt = 0; nt < NT; ++nt, ++acc_it) {
-                    if ((int)(acc_it & 1) != grp) continue;
-                    mbar_wait(&acc_full[grp], (acc_it >> 1) & 1, 0x640 | grp);
+                    const uint32_t buf = acc_it & 1;
+                    mbar_wait(&acc_full[buf], (acc_it >> 1) & 1, 0x640 | buf);
                     tcgen05_fence_after();
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
+                    if (lane == 0) mbar_arrive_cluster(acc_empty_leader0 + buf * 8);
                 }
                 if (MODE == MODE_FWD) asm volatile("bar.sync 3, 256;" ::: "memory");
                 ++it;
@@ -519,36 +520,36 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             }
 
             for (int nt = 0; nt < NT; ++nt, ++acc_it) {
-                if ((int)(acc_it & 1) != grp) continue;  // the other group owns this accumulator buffer
-                const uint32_t acc_phase = (acc_it >> 1) & 1;
+                // both groups work on every accumulator: group g takes columns [g*128, g*128+128), which halves
+                // the time a TMEM buffer stays busy after its last MMA
+                const uint32_t buf = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
+                const uint32_t tmem_row = tmem_row0 + buf * kTileN;
                 // stage bias * log2(e) for this vocabulary tile (one buffer per group).  The values were
                 // loaded into registers while the group's previous tile was being processed, so the L2
                 // latency of the load is off the critical path.
                 {
-                    if (nb_nt != nt) {  // first tile of the kernel for this group
-                        const int v0 = nt * kTileN + gtid, v1 = v0 + 128;
+                    if (nb_nt != nt) {  // first tile of the kernel
+                        const int v0 = nt * kTileN + grp * kGrpCols + gtid;
                         nb0 = v0 < p.V ? __ldg(p.bias + v0) : 0.f;
-                        nb1 = v1 < p.V ? __ldg(p.bias + v1) : 0.f;
                     }
                     asm volatile("bar.sync %0, 128;" ::"r"(4 + grp) : "memory");  // previous tile's reads are done
                     bias_g[gtid] = nb0 * kLog2eF;
-                    bias_g[gtid + 128] = nb1 * kLog2eF;
                     asm volatile("bar.sync %0, 128;" ::"r"(4 + grp) : "memory");
-                    nb_nt = NT >= 2 ? (nt + 2) % NT : 0;  // this group's next vocabulary tile
-                    const int v0 = nb_nt * kTileN + gtid, v1 = v0 + 128;
+                    nb_nt = nt + 1 < NT ? nt + 1 : 0;  // next vocabulary tile
+                    const int v0 = nb_nt * kTileN + grp * kGrpCols + gtid;
                     nb0 = v0 < p.V ? __ldg(p.bias + v0) : 0.f;
-                    nb1 = v1 < p.V ? __ldg(p.bias + v1) : 0.f;
                 }
-                mbar_wait(&acc_full[grp], acc_phase, 0x600 | grp);
+                mbar_wait(&acc_full[buf], acc_phase, 0x600 | buf);
                 tcgen05_fence_after();
-                const int n_cols = nt == NT - 1 ? p.n_last : kTileN;
+                const int n_all = nt == NT - 1 ? p.n_last : kTileN;
+                const int c_begin = grp * kGrpCols, n_cols = min(n_all, c_begin + kGrpCols);  // this group's columns [c_begin, n_cols)
                 // TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c is processed
                 uint32_t raw0[16], raw1[16];
                 auto process = [&](const uint32_t (&raw)[16], const int cc) {
                     const int col0 = nt * kTileN + cc;
                     // y = logit * log2(e) = acc * log2(e) + bias * log2(e), two columns per instruction
                     float2 y2[8];
-                    const float4* b4 = reinterpret_cast<const float4*>(bias_g + cc);
+                    const float4* b4 = reinterpret_cast<const float4*>(bias_g + (cc - c_begin));
                     const float2 l2e = make_float2(kLog2eF, kLog2eF);
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
@@ -651,8 +652,8 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                         }
                     }
                 };
-                tmem_ld_32x32b_x16(tmem_row, raw0);
-                for (int cc = 0; cc < n_cols; cc += 32) {
+                if (c_begin < n_cols) tmem_ld_32x32b_x16(tmem_row + c_begin, raw0);
+                for (int cc = c_begin; cc < n_cols; cc += 32) {
                     tmem_ld_wait();
                     const bool more1 = cc + 16 < n_cols;
                     if (more1) tmem_ld_32x32b_x16(tmem_row + cc + 16, raw1);
@@ -663,11 +664,11 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                         process(raw1, cc + 16);
                     }
                 }
-                if (MODE == MODE_GRAD && n_cols < kTileN) {
+                if (MODE == MODE_GRAD && n_all < kTileN) {
                     // zero-fill the 16-column chunks of the last tile the MMA did not produce, so the
                     // backward GEMMs read finite zeros for the padded vocabulary columns
-                    const int cols_pad = ((p.V + 63) / 64) * 64 - nt * kTileN;  // columns the images cover
-                    for (int cc = n_cols; cc < cols_pad; cc += 16) {
+                    const int cols_pad = min(((p.V + 63) / 64) * 64 - nt * kTileN, c_begin + kGrpCols);  // columns the images cover
+                    for (int cc = max(n_all, c_begin); cc < cols_pad; cc += 16) {
                         const int col0 = nt * kTileN + cc;
                         uint8_t* img = reinterpret_cast<uint8_t*>(p.dY_img) +
                                        ((size_t)(tile - p.tile_begin) * (NT * 4) + (col0 >> 6)) * kABlockBytes;
@@ -681,8 +682,8 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (PAIR && !leader) mbar_arrive_cluster(acc_empty_leader);
-                    else mbar_arrive(&acc_empty[grp]);
+                    if (PAIR && !leader) mbar_arrive_cluster(acc_empty_leader0 + buf * 8);
+                    else mbar_arrive(&acc_empty[buf]);
                 }
             }
             if (MODE == MODE_FWD) {
