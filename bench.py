@@ -49,41 +49,88 @@ def synth(cfg, device, seed=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md "clocks line").
 
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NVML is polled in-process every few milliseconds (the timed region of a default run is ~100 ms, too
+    short for `nvidia-smi -lms`); every sample carries a host timestamp and only samples taken between
+    mark_begin() and mark_end() are reported.  Falls back to one `nvidia-smi` query if NVML is missing."""
 
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def __init__(self, index, period_s=0.004):
+        self.rows, self.t0, self.t1 = [], None, None
+        self.period, self.stop_flag, self.h, self.max_mhz = period_s, False, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) >= 6:
-                self.rows.append(parts)
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001  (no NVML: nvidia-smi fallback in stop())
+            self.h = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001  (older bindings)
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.perf_counter(), float(mhz), int(mask)))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        self.stop_flag = True
+        if self.h is None:
+            return self._smi_once()
+        self.thread.join(timeout=1.0)
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        window = "timed region"
+        if len(rows) < 3:  # very short timed regions: take the nearest samples around it as well
+            rows = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.05]
+            window = "timed region +-50 ms"
+        sm = [r[1] for r in rows]
+        reasons = [n for n, bit in self.REASONS if any(r[2] & bit for r in rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "sm_mhz_min": min(sm) if sm else None, "window": window, "source": "nvml"}
+
+    def _smi_once(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True,
+                                 text=True, timeout=10).stdout.strip().splitlines()[0]
+            parts = [x.strip() for x in out.split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(parts[0]), "sm_max_mhz": float(parts[1]),
+                    "reasons": [n for i, n in enumerate(names) if parts[2 + i].lower().startswith("active")],
+                    "samples": 1, "window": "after the timed region", "source": "nvidia-smi"}
+        except Exception:  # noqa: BLE001
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
 def measured_peaks():
@@ -211,6 +258,7 @@ def main():
             dist.all_reduce(comm)
         return cost
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # polls from the warm-up on; reports the timed window
     for _ in range(W_steps):
         flush.zero_()
         step(False)
@@ -218,9 +266,10 @@ def main():
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = _lib.launch_count()
     evs = []
+    if sampler:
+        sampler.mark_begin()
     for _ in range(K):
         flush.zero_()  # L2 flush between timed iterations (untimed)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -229,6 +278,8 @@ def main():
         e.record()
         evs.append((s, e))
     torch.cuda.synchronize()
+    if sampler:
+        sampler.mark_end()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()

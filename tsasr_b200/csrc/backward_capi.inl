@@ -149,7 +149,13 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
 
     const DjSmem djL = dj_smem_layout();
     const DwSmem dwL = dw_smem_layout();
-    e = cudaFuncSetAttribute(dj_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)djL.total);
+    static const int dj_cs = [] {  // cluster size of the dJ kernel (W boxes are multicast inside the cluster)
+        const char* env = getenv("TSASR_DEBUG_DJ_CLUSTER");
+        const int v = env ? atoi(env) : 2;
+        return (v == 1 || v == 2 || v == 4) ? v : 2;
+    }();
+    auto dj_kern = dj_cs == 4 ? dj_gemm_kernel<4> : (dj_cs == 2 ? dj_gemm_kernel<2> : dj_gemm_kernel<1>);
+    e = cudaFuncSetAttribute(dj_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)djL.total);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dj_gemm_kernel)");
     e = cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dwL.total);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dw_gemm_kernel)");
@@ -163,10 +169,48 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
         jp.tile_end = bp.tile_end = t1;
         if (int rc = launch_joint<MODE_GRAD>(maps, jp, sms, st)) return rc;
 
-        const int n_units = (t1 - t0) * bp.n_hsplit;
-        dj_gemm_kernel<<<n_units < sms ? n_units : sms, kBwdThreads, djL.total, st>>>(tmap_dj, bp);
-        ++g_launches;
-        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "dj_gemm_kernel launch");
+        {
+            const int n_groups = ((t1 - t0 + dj_cs - 1) / dj_cs) * bp.n_hsplit;
+            const int max_clusters = sms / dj_cs;
+            const int n_clusters = n_groups < max_clusters ? n_groups : max_clusters;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(n_clusters * dj_cs);
+            cfg.blockDim = dim3(kBwdThreads);
+            cfg.dynamicSmemBytes = djL.total;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = dj_cs;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            static const bool prof_on = getenv("TSASR_DEBUG_PROF") != nullptr;
+            long long* d_prof = nullptr;
+            BwdParams bpp = bp;
+            if (prof_on) {
+                cudaMalloc(&d_prof, sizeof(long long) * 4 * n_clusters * dj_cs);
+                cudaMemset(d_prof, 0, sizeof(long long) * 4 * n_clusters * dj_cs);
+                bpp.prof = d_prof;
+            }
+            e = cudaLaunchKernelEx(&cfg, dj_kern, tmap_dj, bpp);
+            if (prof_on) {
+                cudaStreamSynchronize(st);
+                const int n = n_clusters * dj_cs;
+                long long* h = new long long[4 * n];
+                cudaMemcpy(h, d_prof, sizeof(long long) * 4 * n, cudaMemcpyDeviceToHost);
+                double tot = 0, acc = 0, full = 0, units = 0;
+                for (int i = 0; i < n; ++i) { tot += h[4 * i]; acc += h[4 * i + 1]; full += h[4 * i + 2]; units += h[4 * i + 3]; }
+                fprintf(stderr, "[tsasr prof] dj cs=%d ctas=%d units/cta=%.1f cycles/cta=%.0f wait: acc_empty=%.1f%% full=%.1f%% other=%.1f%% cycles/unit=%.0f\n",
+                        dj_cs, n, units / n, tot / n, 100 * acc / tot, 100 * full / tot, 100 * (tot - acc - full) / tot, tot / units);
+                delete[] h;
+                cudaFree(d_prof);
+            }
+            ++g_launches;
+            if (e != cudaSuccess) return cuda_fail(e, "dj_gemm_kernel launch");
+            if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "dj_gemm_kernel launch");
+        }
 
         reduce_dpre_enc_kernel<<<sms * 8, 256, 0, st>>>(bp, d_enc);
         reduce_dpre_dec_kernel<<<sms * 8, 256, 0, st>>>(bp, d_dec);

@@ -23,7 +23,9 @@
 namespace tsasr {
 
 static constexpr int kImgBytes = 16384;  // one [128 x 64] bf16 SWIZZLE_128B image
-static constexpr int kBwdThreads = 192;  // warp 0: loads, warp 1: MMA, warps 2-5: epilogue
+static constexpr int kBwdThreads = 192;  // warps 0-3: epilogue, warp 4: loads, warp 5: MMA (highest id = highest issue priority)
+static constexpr int kBwdWarpLoad = 4;
+static constexpr int kBwdWarpMma = 5;
 
 struct BwdParams {
     const int* logit_lengths;
@@ -49,6 +51,7 @@ struct BwdParams {
     int NHT;           // h-tiles of up to 4 h-blocks
     int n_splits;
     int accumulate;    // 0: store, 1: read-modify-write (later chunks)
+    long long* prof;   // development: MMA-warp cycle counters per CTA (or nullptr)
 };
 
 __device__ __forceinline__ bool tile_live(const BwdParams& p, int tile) {
@@ -77,6 +80,13 @@ __host__ __device__ inline DjSmem dj_smem_layout() {
     return l;
 }
 
+// CS = cluster size (1, 2 or 4).  The CS CTAs of a cluster work on CS consecutive cell tiles with the same h-split
+// and therefore consume the SAME W boxes in the same order: every box is fetched from L2 once per cluster
+// (CTA j loads boxes j, j+CS, ... and multicasts them), which divides the dominant W stream by CS.  A stage
+// may be refilled only when every CTA of the cluster has consumed it, so MMA commits are multicast to the
+// `empty` barrier of all CTAs (count CS).  A CTA whose own tile is dead still loads its share of the boxes and
+// commits ("dummy" round).
+template <int CS>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const BwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -89,86 +99,128 @@ dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const BwdParams p) {
     uint64_t* acc_empty = bars + 9;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = CS > 1 ? (int)cluster_ctarank() : 0;
+    const int cluster = CS > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
+    const int n_clusters = CS > 1 ? (int)num_clusters_x() : (int)gridDim.x;
+    constexpr uint16_t kAll = (uint16_t)((1u << CS) - 1);
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();
-        for (int i = 0; i < kDjStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kDjStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CS); }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 4);
         fence_barrier_init();
     }
-    if (warp_idx == 0 && lane == 0) tma_prefetch_desc(&tmap_w);
-    if (warp_idx == 1) tmem_alloc<512>(tmem_ptr);
+    if (warp_idx == kBwdWarpLoad && lane == 0) tma_prefetch_desc(&tmap_w);
+    if (warp_idx == kBwdWarpMma) tmem_alloc<512>(tmem_ptr);
     tcgen05_fence_before();
-    __syncthreads();
+    if (CS > 1) cluster_sync_all();
+    else __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
-    const int n_units = (p.tile_end - p.tile_begin) * p.n_hsplit;
+    const int n_tiles = p.tile_end - p.tile_begin;
+    const int n_groups = ((n_tiles + CS - 1) / CS) * p.n_hsplit;  // (CS consecutive tiles, h-split)
+    // group -> (first tile, h-split, is this CTA's tile live, is any tile of the group live)
+    auto open_group = [&](int g, int& tl, int& hs, bool& my_live) -> bool {
+        const int tg = g / p.n_hsplit;
+        hs = g - tg * p.n_hsplit;
+        tl = tg * CS + rank;
+        my_live = tl < n_tiles && tile_live(p, p.tile_begin + tl);
+        bool any = my_live;
+        if (CS > 1) {
+#pragma unroll
+            for (int r = 0; r < CS; ++r) any |= (tg * CS + r < n_tiles) && tile_live(p, p.tile_begin + tg * CS + r);
+        }
+        return any;
+    };
 
-    if (warp_idx == 0) {
-        if (lane == 0) {
+    if (warp_idx == kBwdWarpLoad) {
+        {  // whole warp, converged; one lane is elected inside each issuing instruction
             uint32_t stage = 0, phase = 0;
-            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-                const int tl = unit / p.n_hsplit, hs = unit - tl * p.n_hsplit;
-                if (!tile_live(p, p.tile_begin + tl)) continue;
+            for (int g = cluster; g < n_groups; g += n_clusters) {
+                int tl, hs;
+                bool my_live;
+                if (!open_group(g, tl, hs, my_live)) continue;
                 const int hb0 = p.hs_kb[hs], nhb = p.hs_kb[hs + 1] - hb0;
                 const uint8_t* dy = reinterpret_cast<const uint8_t*>(p.dY_img) + (size_t)tl * p.NT4 * kImgBytes;
                 for (int vb = 0; vb < p.NVB; ++vb) {
                     mbar_wait(&empty[stage], phase ^ 1, 0x700 | stage);
+                    __syncwarp();
                     uint8_t* st = smem + L.stage_off + stage * kDjStageBytes;
-                    mbar_arrive_expect_tx(&full[stage], kImgBytes + nhb * 8192);
-                    bulk_load_1d(st, dy + (size_t)vb * kImgBytes, kImgBytes, &full[stage]);
-                    for (int j = 0; j < nhb; ++j)
-                        tma_load_2d(st + kImgBytes + j * 8192, &tmap_w, &full[stage], (hb0 + j) * 64, vb * 64);
+                    mbar_arrive_expect_tx_e(&full[stage], (my_live ? kImgBytes : 0) + nhb * 8192);
+                    if (my_live) bulk_load_1d_e(st, dy + (size_t)vb * kImgBytes, kImgBytes, &full[stage]);
+                    for (int j = rank; j < nhb; j += CS) {
+                        if (CS > 1) tma_load_2d_mcast_e(st + kImgBytes + j * 8192, &tmap_w, &full[stage], kAll, (hb0 + j) * 64, vb * 64);
+                        else tma_load_2d_e(st + kImgBytes + j * 8192, &tmap_w, &full[stage], (hb0 + j) * 64, vb * 64);
+                    }
                     if (++stage == kDjStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp_idx == 1) {
-        if (lane == 0) {
+    } else if (warp_idx == kBwdWarpMma) {
+        {  // whole warp, converged
             uint32_t stage = 0, phase = 0, it = 0;
-            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-                const int tl = unit / p.n_hsplit, hs = unit - tl * p.n_hsplit;
-                if (!tile_live(p, p.tile_begin + tl)) continue;
+            long long t_acc = 0, t_full = 0, tm = 0;
+            const long long t_begin = clock64();
+            for (int g = cluster; g < n_groups; g += n_clusters) {
+                int tl, hs;
+                bool my_live;
+                if (!open_group(g, tl, hs, my_live)) continue;
                 const int nhb = p.hs_kb[hs + 1] - p.hs_kb[hs];
                 const int n0 = nhb >= 4 ? 256 : nhb * 64, n1 = (nhb - 4) * 64;  // second MMA covers h-block 4
                 const uint32_t idesc0 = make_idesc_bf16(kTileM, n0, 0, 1);
                 const uint32_t idesc1 = make_idesc_bf16(kTileM, n1 > 0 ? n1 : 64, 0, 1);
-                mbar_wait(acc_empty, (it & 1) ^ 1, 0x800);
-                tcgen05_fence_after();
-                for (int vb = 0; vb < p.NVB; ++vb) {
-                    mbar_wait(&full[stage], phase, 0x900 | stage);
+                if (my_live) {
+                    if (p.prof) tm = clock64();
+                    mbar_wait(acc_empty, (it & 1) ^ 1, 0x800);
+                    if (p.prof) t_acc += clock64() - tm;
                     tcgen05_fence_after();
-                    const uint32_t a_base = smem_u32(smem + L.stage_off + stage * kDjStageBytes);
-                    const uint32_t b_base = a_base + kImgBytes;
+                }
+                for (int vb = 0; vb < p.NVB; ++vb) {
+                    if (p.prof) tm = clock64();
+                    mbar_wait(&full[stage], phase, 0x900 | stage);
+                    if (p.prof) t_full += clock64() - tm;
+                    tcgen05_fence_after();
+                    if (my_live) {
+                        const uint32_t a_base = smem_u32(smem + L.stage_off + stage * kDjStageBytes);
+                        const uint32_t b_base = a_base + kImgBytes;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t a_desc = make_smem_desc_sw128(a_base + k * 32, 0, 1024);          // K-major
-                        const uint64_t b_desc = make_smem_desc_sw128(b_base + k * 2048, 8192, 1024);     // MN-major
-                        umma_bf16(tmem_base, a_desc, b_desc, idesc0, (vb | k) != 0);
-                        if (n1 > 0) {
-                            const uint64_t b_desc1 = make_smem_desc_sw128(b_base + 4 * 8192 + k * 2048, 8192, 1024);
-                            umma_bf16(tmem_base + 256, a_desc, b_desc1, idesc1, (vb | k) != 0);
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t a_desc = make_smem_desc_sw128(a_base + k * 32, 0, 1024);          // K-major
+                            const uint64_t b_desc = make_smem_desc_sw128(b_base + k * 2048, 8192, 1024);     // MN-major
+                            umma_bf16_e(tmem_base, a_desc, b_desc, idesc0, (vb | k) != 0);
+                            if (n1 > 0) {
+                                const uint64_t b_desc1 = make_smem_desc_sw128(b_base + 4 * 8192 + k * 2048, 8192, 1024);
+                                umma_bf16_e(tmem_base + 256, a_desc, b_desc1, idesc1, (vb | k) != 0);
+                            }
                         }
                     }
-                    umma_commit(&empty[stage]);
+                    if (CS > 1) umma_commit_mcast_e(&empty[stage], kAll);  // this CTA is done with the stage
+                    else umma_commit_e(&empty[stage]);
                     if (++stage == kDjStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(acc_full);
-                ++it;
+                if (my_live) {
+                    umma_commit_e(acc_full);
+                    ++it;
+                }
+            }
+            if (p.prof && lane == 0) {
+                long long* o = p.prof + blockIdx.x * 4;
+                o[0] = clock64() - t_begin; o[1] = t_acc; o[2] = t_full; o[3] = it;
             }
         }
     } else {
         const int q = warp_idx & 3;
         const int row = q * 32 + lane;
-        const int e = threadIdx.x - 64;  // 0..127
+        const int e = threadIdx.x;  // 0..127 (epilogue warps 0-3)
         const int col = e & 31, part = e >> 5;
         const int tT = 1 << p.tT_log2, tU = kTileM >> p.tT_log2;
         uint32_t it = 0;
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const int tl = unit / p.n_hsplit, hs = unit - tl * p.n_hsplit;
-            if (!tile_live(p, p.tile_begin + tl)) continue;
+        for (int g = cluster; g < n_groups; g += n_clusters) {
+            int tl, hs;
+            bool my_live;
+            if (!open_group(g, tl, hs, my_live) || !my_live) continue;
             const int h_begin = p.hs_kb[hs] * 64, n_h = (p.hs_kb[hs + 1] - p.hs_kb[hs]) * 64;
             const uint8_t* jimg = reinterpret_cast<const uint8_t*>(p.J_img) + (size_t)tl * p.KB * kImgBytes;
             float* part_out = p.dpre_part + (size_t)tl * (tT + tU) * p.H;
@@ -219,8 +271,9 @@ dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const BwdParams p) {
         }
     }
     tcgen05_fence_before();
-    __syncthreads();
-    if (warp_idx == 1) {
+    if (CS > 1) cluster_sync_all();  // partners may still multicast into this CTA / arrive on its barriers
+    else __syncthreads();
+    if (warp_idx == kBwdWarpMma) {
         tcgen05_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
@@ -326,32 +379,33 @@ dw_gemm_kernel(const BwdParams p) {
             *reinterpret_cast<uint16_t*>(smem + L.ones_off + sw128_offset(threadIdx.x, 0)) = 0x3F80;  // bf16 1.0
         fence_proxy_async_smem();
     }
-    if (warp_idx == 1) tmem_alloc<512>(tmem_ptr);
+    if (warp_idx == kBwdWarpMma) tmem_alloc<512>(tmem_ptr);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
-    if (warp_idx == 0) {
-        if (lane == 0) {
+    if (warp_idx == kBwdWarpLoad) {
+        {
             uint32_t stage = 0, phase = 0;
             for (int tl = split; tl < n_tiles; tl += p.n_splits) {
                 if (!tile_live(p, p.tile_begin + tl)) continue;
                 mbar_wait(&empty[stage], phase ^ 1, 0xB00 | stage);
+                __syncwarp();
                 uint8_t* st = smem + L.stage_off + stage * kDwStageBytes;
                 const uint8_t* dy = reinterpret_cast<const uint8_t*>(p.dY_img) + ((size_t)tl * p.NT4 + vt * 2) * kImgBytes;
                 const uint8_t* jm = reinterpret_cast<const uint8_t*>(p.J_img) + ((size_t)tl * p.KB + hb0) * kImgBytes;
-                mbar_arrive_expect_tx(&full[stage], (2 + nhb) * kImgBytes);
-                bulk_load_1d(st, dy, kImgBytes, &full[stage]);
+                mbar_arrive_expect_tx_e(&full[stage], (2 + nhb) * kImgBytes);
+                bulk_load_1d_e(st, dy, kImgBytes, &full[stage]);
                 // a v-tile whose second 64-column block lies beyond V re-reads the first block: those
                 // accumulator rows (v >= V) are never stored
-                bulk_load_1d(st + kImgBytes, dy + (nvb == 2 ? kImgBytes : 0), kImgBytes, &full[stage]);
-                bulk_load_1d(st + 2 * kImgBytes, jm, nhb * kImgBytes, &full[stage]);
+                bulk_load_1d_e(st + kImgBytes, dy + (nvb == 2 ? kImgBytes : 0), kImgBytes, &full[stage]);
+                bulk_load_1d_e(st + 2 * kImgBytes, jm, nhb * kImgBytes, &full[stage]);
                 if (++stage == kDwStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp_idx == 1) {
-        if (lane == 0) {
+    } else if (warp_idx == kBwdWarpMma) {
+        {  // whole warp, converged
             uint32_t stage = 0, phase = 0;
             bool first = true;
             const uint32_t idesc = make_idesc_bf16(kTileM, nhb * 64, 1, 1);
@@ -367,17 +421,17 @@ dw_gemm_kernel(const BwdParams p) {
                 for (int k = 0; k < 8; ++k) {  // 16 cells per step = two 8-row groups of the image
                     const uint64_t a_desc = make_smem_desc_sw128(a_base + k * 2048, kImgBytes, 1024);  // MN-major, M = v
                     const uint64_t b_desc = make_smem_desc_sw128(b_base + k * 2048, kImgBytes, 1024);  // MN-major, N = h
-                    umma_bf16(tmem_base, a_desc, b_desc, idesc, !(first && k == 0));
+                    umma_bf16_e(tmem_base, a_desc, b_desc, idesc, !(first && k == 0));
                     if (with_db) {
                         const uint64_t o_desc = make_smem_desc_sw128(ones_base + k * 2048, kImgBytes, 1024);
-                        umma_bf16(tmem_base + 256, a_desc, o_desc, idesc_db, !(first && k == 0));
+                        umma_bf16_e(tmem_base + 256, a_desc, o_desc, idesc_db, !(first && k == 0));
                     }
                 }
                 first = false;
-                umma_commit(&empty[stage]);
+                umma_commit_e(&empty[stage]);
                 if (++stage == kDwStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(acc_full);
+            umma_commit_e(acc_full);
         }
     } else {
         const int q = warp_idx & 3;
@@ -427,7 +481,7 @@ dw_gemm_kernel(const BwdParams p) {
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp_idx == 1) {
+    if (warp_idx == kBwdWarpMma) {
         tcgen05_fence_after();
         tmem_dealloc<512>(tmem_base);
     }

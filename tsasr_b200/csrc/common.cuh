@@ -350,6 +350,32 @@ __device__ __forceinline__ void bulk_load_1d_e(void* smem_dst, const void* gsrc,
         ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// Hopper-style multicast inside a cluster (cta_group::1 MMAs): one CTA loads a box and writes it to the same
+// shared offset of every CTA in cta_mask, completing bytes on each destination CTA's own barrier; an MMA
+// commit arrives on the barrier at the same offset of every CTA in cta_mask.
+__device__ __forceinline__ void tma_load_2d_mcast_e(void* smem_dst, const void* tmap, uint64_t* bar, uint16_t cta_mask, int x, int y) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5}], [%2], %3;\n\t}"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "h"(cta_mask), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d_mcast_e(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n\t}"
+        ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast_e(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
 // Shared-memory matrix descriptor (PTX ISA "Matrix Descriptor Format", sm_100 version field = 1).
 //   bits [0,14)  start address >> 4        bits [16,30) leading-dim byte offset >> 4
 //   bits [32,46) stride-dim byte offset >> 4   bits [46,48) version (1)
