@@ -21,6 +21,42 @@ struct BwdPlan {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// development: TSASR_DEBUG_TIMING=1 brackets every backward launch with CUDA events on the launching
+// stream and prints the per-kernel milliseconds to stderr (synchronises; never on in production).
+struct KernelTimer {
+    static constexpr int kMax = 64;
+    bool on;
+    cudaStream_t st;
+    int n = 0;
+    const char* names[kMax];
+    cudaEvent_t ev[kMax + 1];
+    explicit KernelTimer(cudaStream_t s) : st(s) {
+        static const bool enabled = getenv("TSASR_DEBUG_TIMING") != nullptr;
+        on = enabled;
+        if (on) { cudaEventCreate(&ev[0]); cudaEventRecord(ev[0], st); }
+    }
+    void mark(const char* name) {
+        if (!on || n >= kMax) return;
+        names[n] = name;
+        cudaEventCreate(&ev[n + 1]);
+        cudaEventRecord(ev[n + 1], st);
+        ++n;
+    }
+    ~KernelTimer() {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        float total = 0.f;
+        for (int i = 0; i < n; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            total += ms;
+            fprintf(stderr, "[tsasr timing] %-28s %8.3f ms\n", names[i], ms);
+        }
+        fprintf(stderr, "[tsasr timing] %-28s %8.3f ms\n", "backward total", total);
+        for (int i = 0; i <= n; ++i) cudaEventDestroy(ev[i]);
+    }
+};
+
 static void plan_bwd(const JointParams& jp, int num_sms, long long max_chunk_cells, BwdPlan* pl) {
     const int tT = 1 << jp.tT_log2, tU = 128 >> jp.tT_log2;
     const int total_tiles = jp.B * jp.nTt * jp.nTu;
@@ -132,9 +168,9 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
     bp.dW_part = reinterpret_cast<float*>(ws + pl.dY_bytes + pl.J_bytes + pl.part_bytes);
     bp.db_part = reinterpret_cast<float*>(ws + pl.dY_bytes + pl.J_bytes + pl.part_bytes + pl.dW_bytes);
     bp.NVT = pl.NVT; bp.NHT = pl.NHT; bp.n_splits = pl.n_splits;
-    // h-splits of the dJ accumulator (<= 512 TMEM columns, single buffered): one split up to 5 h-blocks
-    if (jp.KB <= 5) { bp.n_hsplit = 1; bp.hs_kb[0] = 0; bp.hs_kb[1] = jp.KB; bp.hs_kb[2] = jp.KB; }
-    else { bp.n_hsplit = 2; bp.hs_kb[0] = 0; bp.hs_kb[1] = (jp.KB + 1) / 2; bp.hs_kb[2] = jp.KB; }
+    bp.enc = reinterpret_cast<const __nv_bfloat16*>(enc);
+    bp.dec = reinterpret_cast<const __nv_bfloat16*>(dec);
+    bp.NHC = (H + kDjChunkH - 1) / kDjChunkH;
 
     JointMaps maps;
     if (int rc = make_joint_maps(&maps, jp, enc, dec, W)) return rc;
@@ -147,14 +183,14 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
     e = cudaMemsetAsync(d_dec, 0, sizeof(float) * (size_t)B * U * H, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(d_dec)");
 
+    // dY operand images as a 2-D tensor [images * 128 rows, 64 v]: an un-swizzled box copies one image verbatim
+    CUtensorMap tmap_dy;
+    if (int rc = make_tmap_2d_bf16(&tmap_dy, jp.dY_img, (uint64_t)pl.chunk_tiles * pl.NT4 * 128, 64, 64, 128, CU_TENSOR_MAP_SWIZZLE_NONE))
+        return rc;
+
     const DjSmem djL = dj_smem_layout();
     const DwSmem dwL = dw_smem_layout();
-    static const int dj_cs = [] {  // cluster size of the dJ kernel (W boxes are multicast inside the cluster)
-        const char* env = getenv("TSASR_DEBUG_DJ_CLUSTER");
-        const int v = env ? atoi(env) : 2;
-        return (v == 1 || v == 2 || v == 4) ? v : 2;
-    }();
-    auto dj_kern = dj_cs == 4 ? dj_gemm_kernel<4> : (dj_cs == 2 ? dj_gemm_kernel<2> : dj_gemm_kernel<1>);
+    auto dj_kern = jp.tT_log2 == 3 ? dj_gemm_kernel<3> : (jp.tT_log2 == 4 ? dj_gemm_kernel<4> : dj_gemm_kernel<5>);
     e = cudaFuncSetAttribute(dj_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)djL.total);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dj_gemm_kernel)");
     e = cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dwL.total);
@@ -163,20 +199,24 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
     const int total_tiles = B * jp.nTt * jp.nTu;
     const int tU = 128 >> jp.tT_log2;
     int chunk_idx = 0;
+    KernelTimer timer(st);
+    timer.mark("memsets");
     for (int t0 = 0; t0 < total_tiles; t0 += pl.chunk_tiles, ++chunk_idx) {
         const int t1 = t0 + pl.chunk_tiles < total_tiles ? t0 + pl.chunk_tiles : total_tiles;
         jp.tile_begin = bp.tile_begin = t0;
         jp.tile_end = bp.tile_end = t1;
         if (int rc = launch_joint<MODE_GRAD>(maps, jp, sms, st)) return rc;
+        timer.mark("joint_gemm<GRAD>");
 
         {
-            const int n_groups = ((t1 - t0 + dj_cs - 1) / dj_cs) * bp.n_hsplit;
+            const int dj_cs = 2;
+            const int n_units = ((t1 - t0 + 1) / 2) * bp.NHC;  // (tile pair, chunk of 256 h-rows)
             const int max_clusters = sms / dj_cs;
-            const int n_clusters = n_groups < max_clusters ? n_groups : max_clusters;
+            const int n_clusters = n_units < max_clusters ? n_units : max_clusters;
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));
             cfg.gridDim = dim3(n_clusters * dj_cs);
-            cfg.blockDim = dim3(kBwdThreads);
+            cfg.blockDim = dim3(kDjThreads);
             cfg.dynamicSmemBytes = djL.total;
             cfg.stream = st;
             cudaLaunchAttribute attr[1];
@@ -194,38 +234,44 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
                 cudaMemset(d_prof, 0, sizeof(long long) * 4 * n_clusters * dj_cs);
                 bpp.prof = d_prof;
             }
-            e = cudaLaunchKernelEx(&cfg, dj_kern, tmap_dj, bpp);
+            e = cudaLaunchKernelEx(&cfg, dj_kern, tmap_dj, tmap_dy, bpp);
             if (prof_on) {
                 cudaStreamSynchronize(st);
                 const int n = n_clusters * dj_cs;
                 long long* h = new long long[4 * n];
                 cudaMemcpy(h, d_prof, sizeof(long long) * 4 * n, cudaMemcpyDeviceToHost);
                 double tot = 0, acc = 0, full = 0, units = 0;
-                for (int i = 0; i < n; ++i) { tot += h[4 * i]; acc += h[4 * i + 1]; full += h[4 * i + 2]; units += h[4 * i + 3]; }
-                fprintf(stderr, "[tsasr prof] dj cs=%d ctas=%d units/cta=%.1f cycles/cta=%.0f wait: acc_empty=%.1f%% full=%.1f%% other=%.1f%% cycles/unit=%.0f\n",
-                        dj_cs, n, units / n, tot / n, 100 * acc / tot, 100 * full / tot, 100 * (tot - acc - full) / tot, tot / units);
+                int nl = 0;
+                for (int i = 0; i < n; ++i)
+                    if (h[4 * i] > 0) { tot += h[4 * i]; acc += h[4 * i + 1]; full += h[4 * i + 2]; units += h[4 * i + 3]; ++nl; }
+                fprintf(stderr, "[tsasr prof] dj issuing ctas=%d units/cta=%.1f cycles/cta=%.0f wait: acc_empty=%.1f%% full=%.1f%% other=%.1f%% cycles/unit=%.0f\n",
+                        nl, units / nl, tot / nl, 100 * acc / tot, 100 * full / tot, 100 * (tot - acc - full) / tot, tot / units);
                 delete[] h;
                 cudaFree(d_prof);
             }
             ++g_launches;
             if (e != cudaSuccess) return cuda_fail(e, "dj_gemm_kernel launch");
             if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "dj_gemm_kernel launch");
+            timer.mark("dj_gemm");
         }
 
         reduce_dpre_enc_kernel<<<sms * 8, 256, 0, st>>>(bp, d_enc);
         reduce_dpre_dec_kernel<<<sms * 8, 256, 0, st>>>(bp, d_dec);
         g_launches += 2;
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "reduce_dpre kernels launch");
+        timer.mark("reduce_dpre_enc+dec");
 
         bp.accumulate = chunk_idx > 0;
         dw_gemm_kernel<<<pl.NVT * pl.NHT * pl.n_splits, kBwdThreads, dwL.total, st>>>(bp);
         ++g_launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "dw_gemm_kernel launch");
+        timer.mark("dw_gemm");
     }
     (void)tU;
     reduce_dw_kernel<<<sms * 2, 256, 0, st>>>(bp, dW, db);
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "reduce_dw_kernel launch");
+    timer.mark("reduce_dw");
     return TSASR_OK;
 }
 

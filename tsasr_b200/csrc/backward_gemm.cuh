@@ -23,7 +23,7 @@
 namespace tsasr {
 
 static constexpr int kImgBytes = 16384;  // one [128 x 64] bf16 SWIZZLE_128B image
-static constexpr int kBwdThreads = 192;  // warps 0-3: epilogue, warp 4: loads, warp 5: MMA (highest id = highest issue priority)
+static constexpr int kBwdThreads = 192;  // dW kernel: warps 0-3: epilogue, warp 4: loads, warp 5: MMA (highest id = highest issue priority)
 static constexpr int kBwdWarpLoad = 4;
 static constexpr int kBwdWarpMma = 5;
 
@@ -41,9 +41,10 @@ struct BwdParams {
     const __nv_bfloat16* dY_img;
     const __nv_bfloat16* J_img;
     // dJ
+    const __nv_bfloat16* enc;  // [B,T,H]
+    const __nv_bfloat16* dec;  // [B,U,H]
     float* dpre_part;  // [tile - tile_begin][tT + tU][H]
-    int n_hsplit;      // 1 or 2
-    int hs_kb[3];      // split s covers h-blocks [hs_kb[s], hs_kb[s+1])
+    int NHC;           // ceil(H / 256): chunks of h-rows per tile pair
     // dW
     float* dW_part;    // [n_splits][NVT * 128][H]
     float* db_part;    // [n_splits][NVT * 128]
@@ -63,147 +64,200 @@ __device__ __forceinline__ bool tile_live(const BwdParams& p, int tile) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// dJ GEMM + activation backward + in-tile broadcast-sum reductions
+// dJ GEMM (transposed) + activation backward + in-register broadcast-sum reductions
 // ------------------------------------------------------------------------------------------------
-static constexpr int kDjStages = 3;
-static constexpr int kDjStageBytes = kImgBytes + 5 * 8192;  // dY image + up to 5 W boxes [64 v x 64 h]
-static constexpr int kDjStagingFloats = 128 * 33;
+// The GEMM is computed TRANSPOSED, dJ^T[h, cell] = sum_v W[v, h] * dY[cell, v], on CTA pairs
+// (tcgen05 cta_group::2, M = 256 h-rows x N = 256 cells = two cell tiles, K = v):
+//   A = W^T   MN-major: per k-block two TMA boxes [64 v x 64 h] SWIZZLE_128B per CTA (its own 128 h-rows)
+//   B = dY    K-major : the [128 cells x 64 v] operand image of the CTA's own cell tile (tile 2i + rank)
+// so a TMEM lane is one h and the 128 columns of a tile are its cells.  Both broadcast-sum reductions
+// of transducer_joint.py:74 (sum over u -> d_enc row, sum over t -> d_dec row) are then plain
+// in-register adds along the columns of a thread, act'(enc[t,h] + dec[u,h]) needs 24 scalars per thread,
+// and the per-tile partial rows are stored h-contiguous (one 128-byte line per warp store).
+// Unit of work = (tile pair, chunk of 256 h-rows); H = 640 runs three chunks, the upper half of the last
+// one is padding (its CTA only supplies its dY image).  Accumulators are double-buffered (2 x 256 TMEM
+// columns), so the epilogue of a unit overlaps the MMAs of the next.
+static constexpr int kDjStages = 5;
+static constexpr int kDjStageBytes = 2 * 8192 + kImgBytes;  // two W boxes + one dY image
+static constexpr int kDjThreads = 320;  // warps 0-7: epilogue, warp 8: loads, warp 9: MMA (leader CTA)
+static constexpr int kDjWarpLoad = 8;
+static constexpr int kDjWarpMma = 9;
+static constexpr int kDjChunkH = 256;
 
-struct DjSmem { uint32_t stage_off, staging_off, bar_off, tmem_off, total; };
+struct DjSmem { uint32_t stage_off, bar_off, tmem_off, total; };
 __host__ __device__ inline DjSmem dj_smem_layout() {
     DjSmem l;
     l.stage_off = 0;
-    l.staging_off = kDjStages * kDjStageBytes;
-    l.bar_off = l.staging_off + 2 * kDjStagingFloats * 4;
+    l.bar_off = kDjStages * kDjStageBytes;
     l.tmem_off = l.bar_off + 16 * 8;
     l.total = l.tmem_off + 16;
     return l;
 }
 
-// CS = cluster size (1, 2 or 4).  The CS CTAs of a cluster work on CS consecutive cell tiles with the same h-split
-// and therefore consume the SAME W boxes in the same order: every box is fetched from L2 once per cluster
-// (CTA j loads boxes j, j+CS, ... and multicasts them), which divides the dominant W stream by CS.  A stage
-// may be refilled only when every CTA of the cluster has consumed it, so MMA commits are multicast to the
-// `empty` barrier of all CTAs (count CS).  A CTA whose own tile is dead still loads its share of the boxes and
-// commits ("dummy" round).
-template <int CS>
-__global__ void __launch_bounds__(kBwdThreads, 1)
-dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const BwdParams p) {
+// four K = 16 steps of one stage: A (MN-major) advances by 16 v-rows = 2048 B, B (K-major) by 32 B
+__device__ __forceinline__ void umma_bf16_2cta_x4_mnA_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                        uint32_t accumulate_first) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "add.u64 a1, %1, 128;\n\tadd.u64 a2, %1, 256;\n\tadd.u64 a3, %1, 384;\n\t"
+        "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, t;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, t;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, t;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta_e(void* smem_dst, const void* tmap, uint32_t mbar_cluster, int x, int y) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(mbar_cluster), "r"(x), "r"(y) : "memory");
+}
+
+// act'(x) of the pre-activation x = enc + dec, evaluated exactly as the forward does it: the derivative is
+// taken at the bf16-rounded activation output (sign for (leaky) ReLU, 1 - J^2 for tanh).
+template <int ACT>
+__device__ __forceinline__ float act_grad_pre(float x, float param) {
+    if (ACT == ACT_LEAKY_RELU) return x > 0.f ? 1.f : param;
+    if (ACT == ACT_RELU) return x > 0.f ? 1.f : 0.f;
+    if (ACT == ACT_TANH) {
+        const float j = __bfloat162float(__float2bfloat16_rn(tanhf(x)));
+        return 1.f - j * j;
+    }
+    return 1.f;
+}
+
+// Epilogue of one (tile, 32 h-rows) slab: thread = one h, registers = the tile's 128 cells.
+template <int TT_LOG2, int ACT>
+__device__ __forceinline__ void dj_epilogue_tile(const BwdParams& p, uint32_t tmem_addr, const float (&e)[1 << TT_LOG2],
+                                                 const float (&d)[128 >> TT_LOG2], float* __restrict__ out_h) {
+    constexpr int TT = 1 << TT_LOG2, TU = 128 >> TT_LOG2;
+    float acc_e[TT], acc_d[TU];
+#pragma unroll
+    for (int i = 0; i < TT; ++i) acc_e[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < TU; ++i) acc_d[i] = 0.f;
+    uint32_t raw0[32], raw1[32];
+    auto consume = [&](const uint32_t (&raw)[32], const int j) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int r = 32 * j + i;  // tile row = ui * TT + ti
+            const int ti = r & (TT - 1), ui = r >> TT_LOG2;
+            const float v = __uint_as_float(raw[i]) * act_grad_pre<ACT>(e[ti] + d[ui], p.act_param);
+            acc_e[ti] += v;
+            acc_d[ui] += v;
+        }
+    };
+    tmem_ld_32x32b_x32(tmem_addr, raw0);
+    tmem_ld_wait();
+    tmem_ld_32x32b_x32(tmem_addr + 32, raw1);
+    consume(raw0, 0);
+    tmem_ld_wait();
+    tmem_ld_32x32b_x32(tmem_addr + 64, raw0);
+    consume(raw1, 1);
+    tmem_ld_wait();
+    tmem_ld_32x32b_x32(tmem_addr + 96, raw1);
+    consume(raw0, 2);
+    tmem_ld_wait();
+    consume(raw1, 3);
+#pragma unroll
+    for (int i = 0; i < TT; ++i) out_h[(size_t)i * p.H] = acc_e[i];
+#pragma unroll
+    for (int i = 0; i < TU; ++i) out_h[(size_t)(TT + i) * p.H] = acc_d[i];
+}
+
+template <int TT_LOG2>
+__global__ void __launch_bounds__(kDjThreads, 1)
+dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_dy, const BwdParams p) {
+    constexpr int TT = 1 << TT_LOG2, TU = 128 >> TT_LOG2;
     extern __shared__ __align__(1024) uint8_t smem[];
     const DjSmem L = dj_smem_layout();
-    float* staging = reinterpret_cast<float*>(smem + L.staging_off);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
-    uint64_t* full = bars;             // [kDjStages]
-    uint64_t* empty = bars + 4;        // [kDjStages]
-    uint64_t* acc_full = bars + 8;
-    uint64_t* acc_empty = bars + 9;
+    uint64_t* full = bars;              // [kDjStages]  leader: bytes of BOTH CTAs' loads
+    uint64_t* empty = bars + 5;         // [kDjStages]  every CTA: the pair's MMAs are done with the stage
+    uint64_t* acc_full = bars + 10;     // [2]          every CTA: accumulator buffer complete
+    uint64_t* acc_empty = bars + 12;    // [2]          leader: 16 epilogue warps released the buffer
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rank = CS > 1 ? (int)cluster_ctarank() : 0;
-    const int cluster = CS > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
-    const int n_clusters = CS > 1 ? (int)num_clusters_x() : (int)gridDim.x;
-    constexpr uint16_t kAll = (uint16_t)((1u << CS) - 1);
+    const int rank = (int)cluster_ctarank();
+    const int cluster = (int)cluster_id_x(), n_clusters = (int)num_clusters_x();
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();
-        for (int i = 0; i < kDjStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CS); }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 4);
+        for (int i = 0; i < kDjStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
         fence_barrier_init();
     }
-    if (warp_idx == kBwdWarpLoad && lane == 0) tma_prefetch_desc(&tmap_w);
-    if (warp_idx == kBwdWarpMma) tmem_alloc<512>(tmem_ptr);
+    if (warp_idx == kDjWarpLoad && lane == 0) { tma_prefetch_desc(&tmap_w); tma_prefetch_desc(&tmap_dy); }
+    if (warp_idx == kDjWarpMma) tmem_alloc_2cta<512>(tmem_ptr);
     tcgen05_fence_before();
-    if (CS > 1) cluster_sync_all();
-    else __syncthreads();
+    cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
     const int n_tiles = p.tile_end - p.tile_begin;
-    const int n_groups = ((n_tiles + CS - 1) / CS) * p.n_hsplit;  // (CS consecutive tiles, h-split)
-    // group -> (first tile, h-split, is this CTA's tile live, is any tile of the group live)
-    auto open_group = [&](int g, int& tl, int& hs, bool& my_live) -> bool {
-        const int tg = g / p.n_hsplit;
-        hs = g - tg * p.n_hsplit;
-        tl = tg * CS + rank;
-        my_live = tl < n_tiles && tile_live(p, p.tile_begin + tl);
-        bool any = my_live;
-        if (CS > 1) {
-#pragma unroll
-            for (int r = 0; r < CS; ++r) any |= (tg * CS + r < n_tiles) && tile_live(p, p.tile_begin + tg * CS + r);
-        }
-        return any;
-    };
+    const int n_pairs = (n_tiles + 1) >> 1;
+    const int n_units = n_pairs * p.NHC;  // consecutive units = the h-chunks of one tile pair (they share the dY images in L2)
+    auto live_local = [&](int tl) { return tl < n_tiles && tile_live(p, p.tile_begin + tl); };
 
-    if (warp_idx == kBwdWarpLoad) {
-        {  // whole warp, converged; one lane is elected inside each issuing instruction
-            uint32_t stage = 0, phase = 0;
-            for (int g = cluster; g < n_groups; g += n_clusters) {
-                int tl, hs;
-                bool my_live;
-                if (!open_group(g, tl, hs, my_live)) continue;
-                const int hb0 = p.hs_kb[hs], nhb = p.hs_kb[hs + 1] - hb0;
-                const uint8_t* dy = reinterpret_cast<const uint8_t*>(p.dY_img) + (size_t)tl * p.NT4 * kImgBytes;
-                for (int vb = 0; vb < p.NVB; ++vb) {
-                    mbar_wait(&empty[stage], phase ^ 1, 0x700 | stage);
-                    __syncwarp();
-                    uint8_t* st = smem + L.stage_off + stage * kDjStageBytes;
-                    mbar_arrive_expect_tx_e(&full[stage], (my_live ? kImgBytes : 0) + nhb * 8192);
-                    if (my_live) bulk_load_1d_e(st, dy + (size_t)vb * kImgBytes, kImgBytes, &full[stage]);
-                    for (int j = rank; j < nhb; j += CS) {
-                        if (CS > 1) tma_load_2d_mcast_e(st + kImgBytes + j * 8192, &tmap_w, &full[stage], kAll, (hb0 + j) * 64, vb * 64);
-                        else tma_load_2d_e(st + kImgBytes + j * 8192, &tmap_w, &full[stage], (hb0 + j) * 64, vb * 64);
-                    }
-                    if (++stage == kDjStages) { stage = 0; phase ^= 1; }
-                }
+    if (warp_idx == kDjWarpLoad) {
+        // ===================== loads (whole warp, converged; one lane elected per instruction) =====================
+        uint32_t stage = 0, phase = 0;
+        const uint32_t full0 = mapa_u32(smem_u32(&full[0]), 0);  // the leader's barriers
+        for (int unit = cluster; unit < n_units; unit += n_clusters) {
+            const int pi = unit / p.NHC, c = unit - pi * p.NHC;
+            const bool live0 = live_local(2 * pi), live1 = live_local(2 * pi + 1);
+            if (!live0 && !live1) continue;
+            const int hbase = c * kDjChunkH;
+            const int nbox0 = max(0, min(2, (p.H - hbase) >> 6)), nbox1 = max(0, min(2, (p.H - hbase - 128) >> 6));
+            const bool my_live = rank ? live1 : live0;
+            const int my_nbox = rank ? nbox1 : nbox0, h0 = hbase + rank * 128;
+            const uint32_t bytes_pair = (uint32_t)(nbox0 + nbox1) * 8192u + (uint32_t)((int)live0 + (int)live1) * kImgBytes;
+            const int img_row0 = (2 * pi + rank) * p.NT4 * 128;
+            for (int kb = 0; kb < p.NVB; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1, 0x700 | stage);
+                __syncwarp();
+                uint8_t* st = smem + L.stage_off + stage * kDjStageBytes;
+                if (rank == 0) mbar_arrive_expect_tx_e(&full[stage], bytes_pair);
+                for (int j = 0; j < my_nbox; ++j) tma_load_2d_2cta_e(st + j * 8192, &tmap_w, full0 + stage * 8, h0 + j * 64, kb * 64);
+                if (my_live) tma_load_2d_2cta_e(st + 2 * 8192, &tmap_dy, full0 + stage * 8, 0, img_row0 + kb * 128);
+                if (++stage == kDjStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp_idx == kBwdWarpMma) {
-        {  // whole warp, converged
+    } else if (warp_idx == kDjWarpMma) {
+        // ===================== MMA issue (leader CTA; whole warp, converged) =====================
+        if (rank == 0) {
             uint32_t stage = 0, phase = 0, it = 0;
+            const uint32_t idesc = make_idesc_bf16(256, 256, 1, 0);
+            const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smem + L.stage_off), 8192, 1024);          // MN-major
+            const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem + L.stage_off) + 2 * 8192, 0, 1024);   // K-major
             long long t_acc = 0, t_full = 0, tm = 0;
             const long long t_begin = clock64();
-            for (int g = cluster; g < n_groups; g += n_clusters) {
-                int tl, hs;
-                bool my_live;
-                if (!open_group(g, tl, hs, my_live)) continue;
-                const int nhb = p.hs_kb[hs + 1] - p.hs_kb[hs];
-                const int n0 = nhb >= 4 ? 256 : nhb * 64, n1 = (nhb - 4) * 64;  // second MMA covers h-block 4
-                const uint32_t idesc0 = make_idesc_bf16(kTileM, n0, 0, 1);
-                const uint32_t idesc1 = make_idesc_bf16(kTileM, n1 > 0 ? n1 : 64, 0, 1);
-                if (my_live) {
-                    if (p.prof) tm = clock64();
-                    mbar_wait(acc_empty, (it & 1) ^ 1, 0x800);
-                    if (p.prof) t_acc += clock64() - tm;
-                    tcgen05_fence_after();
-                }
-                for (int vb = 0; vb < p.NVB; ++vb) {
+            for (int unit = cluster; unit < n_units; unit += n_clusters) {
+                const int pi = unit / p.NHC;
+                if (!live_local(2 * pi) && !live_local(2 * pi + 1)) continue;
+                const uint32_t buf = it & 1;
+                if (p.prof) tm = clock64();
+                mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 0x800 | buf);
+                if (p.prof) t_acc += clock64() - tm;
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 256;
+                for (int kb = 0; kb < p.NVB; ++kb) {
                     if (p.prof) tm = clock64();
                     mbar_wait(&full[stage], phase, 0x900 | stage);
                     if (p.prof) t_full += clock64() - tm;
                     tcgen05_fence_after();
-                    if (my_live) {
-                        const uint32_t a_base = smem_u32(smem + L.stage_off + stage * kDjStageBytes);
-                        const uint32_t b_base = a_base + kImgBytes;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t a_desc = make_smem_desc_sw128(a_base + k * 32, 0, 1024);          // K-major
-                            const uint64_t b_desc = make_smem_desc_sw128(b_base + k * 2048, 8192, 1024);     // MN-major
-                            umma_bf16_e(tmem_base, a_desc, b_desc, idesc0, (vb | k) != 0);
-                            if (n1 > 0) {
-                                const uint64_t b_desc1 = make_smem_desc_sw128(b_base + 4 * 8192 + k * 2048, 8192, 1024);
-                                umma_bf16_e(tmem_base + 256, a_desc, b_desc1, idesc1, (vb | k) != 0);
-                            }
-                        }
-                    }
-                    if (CS > 1) umma_commit_mcast_e(&empty[stage], kAll);  // this CTA is done with the stage
-                    else umma_commit_e(&empty[stage]);
+                    const uint64_t off = (uint64_t)(stage * (kDjStageBytes >> 4));
+                    umma_bf16_2cta_x4_mnA_e(d_tmem, a_desc0 + off, b_desc0 + off, idesc, kb != 0);
+                    umma_commit_2cta_e(&empty[stage], 3);
                     if (++stage == kDjStages) { stage = 0; phase ^= 1; }
                 }
-                if (my_live) {
-                    umma_commit_e(acc_full);
-                    ++it;
-                }
+                umma_commit_2cta_e(&acc_full[buf], 3);
+                ++it;
             }
             if (p.prof && lane == 0) {
                 long long* o = p.prof + blockIdx.x * 4;
@@ -211,71 +265,58 @@ dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const BwdParams p) {
             }
         }
     } else {
-        const int q = warp_idx & 3;
-        const int row = q * 32 + lane;
-        const int e = threadIdx.x;  // 0..127 (epilogue warps 0-3)
-        const int col = e & 31, part = e >> 5;
-        const int tT = 1 << p.tT_log2, tU = kTileM >> p.tT_log2;
+        // ===================== epilogue: warps 0-7, lane quarter q, cell tile g of the pair =====================
+        const int q = warp_idx & 3, g = warp_idx >> 2;
+        const uint32_t acc_empty0 = mapa_u32(smem_u32(&acc_empty[0]), 0);
+        const int per_b = p.nTt * p.nTu;
         uint32_t it = 0;
-        for (int g = cluster; g < n_groups; g += n_clusters) {
-            int tl, hs;
-            bool my_live;
-            if (!open_group(g, tl, hs, my_live) || !my_live) continue;
-            const int h_begin = p.hs_kb[hs] * 64, n_h = (p.hs_kb[hs + 1] - p.hs_kb[hs]) * 64;
-            const uint8_t* jimg = reinterpret_cast<const uint8_t*>(p.J_img) + (size_t)tl * p.KB * kImgBytes;
-            float* part_out = p.dpre_part + (size_t)tl * (tT + tU) * p.H;
-            mbar_wait(acc_full, it & 1, 0xA00);
+        for (int unit = cluster; unit < n_units; unit += n_clusters) {
+            const int pi = unit / p.NHC, c = unit - pi * p.NHC;
+            const bool live0 = live_local(2 * pi), live1 = live_local(2 * pi + 1);
+            if (!live0 && !live1) continue;
+            const uint32_t buf = it & 1;
+            const int tl = 2 * pi + g;
+            const int h = c * kDjChunkH + rank * 128 + q * 32 + lane;
+            const bool work = (g ? live1 : live0) && (h - lane) < p.H;  // warp-uniform
+            float e[TT], d[TU];
+            if (work) {
+                // the 24 pre-activation scalars of this thread's h (clamped rows: cells beyond T/U carry zero dY)
+                const int tile = p.tile_begin + tl;
+                const int b = tile / per_b, rem = tile - b * per_b;
+                const int tt = rem / p.nTu, tu = rem - tt * p.nTu;
+                const __nv_bfloat16* er = p.enc + ((size_t)b * p.T) * p.H + h;
+                const __nv_bfloat16* dr = p.dec + ((size_t)b * p.U) * p.H + h;
+#pragma unroll
+                for (int i = 0; i < TT; ++i) e[i] = __bfloat162float(er[(size_t)min(tt * TT + i, p.T - 1) * p.H]);
+#pragma unroll
+                for (int i = 0; i < TU; ++i) d[i] = __bfloat162float(dr[(size_t)min(tu * TU + i, p.U - 1) * p.H]);
+            }
+            mbar_wait(&acc_full[buf], (it >> 1) & 1, 0xA00 | buf);
             tcgen05_fence_after();
-            for (int cc = 0, ci = 0; cc < n_h; cc += 32, ++ci) {
-                uint32_t raw[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + cc, raw);
-                // activation outputs of this row: 32 bf16 = 4 chunks of the J image
-                const int h = h_begin + cc;
-                const uint8_t* jb = jimg + (size_t)(h >> 6) * kImgBytes;
-                uint4 jv[4];
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4)
-                    jv[c4] = *reinterpret_cast<const uint4*>(jb + sw128_offset((uint32_t)row, (uint32_t)(((h & 63) >> 3) + c4)));
-                tmem_ld_wait();
-                float* sbuf = staging + (ci & 1) * kDjStagingFloats;
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const uint32_t* w = reinterpret_cast<const uint32_t*>(&jv[c4]);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int j = c4 * 8 + k * 2;
-                        sbuf[row * 33 + j] = __uint_as_float(raw[j]) * act_grad_from_output(bf16_lo(w[k]), p.act_kind, p.act_param);
-                        sbuf[row * 33 + j + 1] = __uint_as_float(raw[j + 1]) * act_grad_from_output(bf16_hi(w[k]), p.act_kind, p.act_param);
-                    }
+            if (work) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + g * 128;
+                float* out_h = p.dpre_part + (size_t)tl * (TT + TU) * p.H + h;
+                switch (p.act_kind) {
+                    case ACT_LEAKY_RELU: dj_epilogue_tile<TT_LOG2, ACT_LEAKY_RELU>(p, taddr, e, d, out_h); break;
+                    case ACT_RELU: dj_epilogue_tile<TT_LOG2, ACT_RELU>(p, taddr, e, d, out_h); break;
+                    case ACT_TANH: dj_epilogue_tile<TT_LOG2, ACT_TANH>(p, taddr, e, d, out_h); break;
+                    default: dj_epilogue_tile<TT_LOG2, ACT_IDENTITY>(p, taddr, e, d, out_h); break;
                 }
-                asm volatile("bar.sync 2, 128;" ::: "memory");
-                // sum over ui (rows ui*tT + ti) -> d_enc partial row ti; sum over ti -> d_dec partial row ui
-                for (int ti = part; ti < tT; ti += 4) {
-                    float s = 0.f;
-                    for (int ui = 0; ui < tU; ++ui) s += sbuf[(ui * tT + ti) * 33 + col];
-                    part_out[(size_t)ti * p.H + h + col] = s;
-                }
-                for (int ui = part; ui < tU; ui += 4) {
-                    float s = 0.f;
-                    for (int ti = 0; ti < tT; ++ti) s += sbuf[(ui * tT + ti) * 33 + col];
-                    part_out[(size_t)(tT + ui) * p.H + h + col] = s;
-                }
-                // staging is double-buffered: the next chunk writes the other buffer, and the barrier of
-                // the next chunk orders these reads before that buffer is written again
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty);
-            asm volatile("bar.sync 2, 128;" ::: "memory");  // staging buffers are free again
+            if (lane == 0) {
+                if (rank) mbar_arrive_cluster(acc_empty0 + buf * 8);
+                else mbar_arrive(&acc_empty[buf]);
+            }
             ++it;
         }
     }
     tcgen05_fence_before();
-    if (CS > 1) cluster_sync_all();  // partners may still multicast into this CTA / arrive on its barriers
-    else __syncthreads();
-    if (warp_idx == kBwdWarpMma) {
+    cluster_sync_all();  // the partner may still signal this CTA's barriers / read its shared memory
+    if (warp_idx == kDjWarpMma) {
         tcgen05_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        tmem_dealloc_2cta<512>(tmem_base);
     }
 }
 
