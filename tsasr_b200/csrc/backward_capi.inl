@@ -14,8 +14,8 @@ static constexpr size_t kDefaultChunkBytes = (size_t)3 << 30;  // 3 GiB of opera
 struct BwdPlan {
     int chunk_tiles;      // multiple of nTu
     int n_chunks;
-    int n_splits;
-    int NVT, NHT, NVB, NT4;
+    int NV2, NHU, NVB, NT4;
+    int hu_blk[3], hu_splits[3], hu_pair0[3], max_splits;
     size_t dY_bytes, J_bytes, part_bytes, dW_bytes, db_bytes, total;
 };
 
@@ -79,17 +79,51 @@ static void plan_bwd(const JointParams& jp, int num_sms, long long max_chunk_cel
         const int gpc = (total_groups + pl->n_chunks - 1) / pl->n_chunks;
         pl->chunk_tiles = gpc * jp.nTu;
     }
-    pl->NVT = (jp.V + 127) / 128;
-    pl->NHT = (jp.KB + 3) / 4;
-    int splits = num_sms / (pl->NVT * pl->NHT);
-    if (splits < 1) splits = 1;
-    if (splits > pl->chunk_tiles) splits = pl->chunk_tiles;
-    pl->n_splits = splits;
+    // dW work decomposition: (256 v-rows) x (h-unit) x (split-K), one CTA pair each
+    pl->NV2 = (jp.V + 255) / 256;
+    {
+        const int KBe = (jp.KB + 1) & ~1;
+        pl->hu_blk[0] = 0;
+        if (KBe <= 6) { pl->NHU = 1; pl->hu_blk[1] = jp.KB; pl->hu_blk[2] = jp.KB; }
+        else { pl->NHU = 2; pl->hu_blk[1] = KBe - 2 < 8 ? KBe - 2 : 8; pl->hu_blk[2] = jp.KB; }
+        // split-K factors proportional to the measured cycles per pipeline stage of a unit (config 2, L2-bound:
+        // ~580 + 157 per J half-image slot), so that all units sweep the tiles at the same pace and finish together
+        const int pairs = num_sms / 2;
+        int w[2] = {0, 0}, wsum = 0;
+        for (int u = 0; u < pl->NHU; ++u) {
+            const int nblk_e = (pl->hu_blk[u + 1] - pl->hu_blk[u] + 1) & ~1;
+            w[u] = 580 + 157 * (nblk_e / 2);
+        }
+        if (const char* env = getenv("TSASR_DEBUG_DW_WEIGHTS")) sscanf(env, "%d,%d", &w[0], &w[1]);  // development knob
+        for (int u = 0; u < pl->NHU; ++u) wsum += w[u];
+        for (int u = 0; u < pl->NHU; ++u) {
+            int sp = pairs * w[u] / (wsum * pl->NV2);
+            pl->hu_splits[u] = sp < 1 ? 1 : sp;
+        }
+        pl->hu_splits[pl->NHU] = 0;
+        for (;;) {  // hand leftover pairs to the most loaded unit
+            int used = 0, worst = 0;
+            for (int u = 0; u < pl->NHU; ++u) {
+                used += pl->hu_splits[u] * pl->NV2;
+                if ((long long)w[u] * pl->hu_splits[worst] > (long long)w[worst] * pl->hu_splits[u]) worst = u;
+            }
+            if (used + pl->NV2 > pairs) break;
+            ++pl->hu_splits[worst];
+        }
+        pl->max_splits = 1;
+        pl->hu_pair0[0] = 0;
+        for (int u = 0; u < pl->NHU; ++u) {
+            if (pl->hu_splits[u] > pl->chunk_tiles) pl->hu_splits[u] = pl->chunk_tiles;
+            pl->hu_pair0[u + 1] = pl->hu_pair0[u] + pl->hu_splits[u] * pl->NV2;
+            if (pl->hu_splits[u] > pl->max_splits) pl->max_splits = pl->hu_splits[u];
+        }
+        if (pl->NHU == 1) pl->hu_pair0[2] = pl->hu_pair0[1];
+    }
     pl->dY_bytes = align_up((size_t)pl->chunk_tiles * pl->NT4 * kImgBytes, 1024);
     pl->J_bytes = align_up((size_t)pl->chunk_tiles * jp.KB * kImgBytes, 1024);
     pl->part_bytes = align_up((size_t)pl->chunk_tiles * (tT + tU) * jp.H * 4, 1024);
-    pl->dW_bytes = align_up((size_t)pl->n_splits * pl->NVT * 128 * jp.H * 4, 1024);
-    pl->db_bytes = align_up((size_t)pl->n_splits * pl->NVT * 128 * 4, 1024);
+    pl->dW_bytes = align_up((size_t)pl->max_splits * pl->NV2 * 256 * jp.H * 4, 1024);
+    pl->db_bytes = align_up((size_t)pl->max_splits * pl->NV2 * 256 * 4, 1024);
     pl->total = pl->dY_bytes + pl->J_bytes + pl->part_bytes + pl->dW_bytes + pl->db_bytes + 1024;
 }
 
@@ -167,7 +201,9 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
     bp.dpre_part = reinterpret_cast<float*>(ws + pl.dY_bytes + pl.J_bytes);
     bp.dW_part = reinterpret_cast<float*>(ws + pl.dY_bytes + pl.J_bytes + pl.part_bytes);
     bp.db_part = reinterpret_cast<float*>(ws + pl.dY_bytes + pl.J_bytes + pl.part_bytes + pl.dW_bytes);
-    bp.NVT = pl.NVT; bp.NHT = pl.NHT; bp.n_splits = pl.n_splits;
+    bp.NV2 = pl.NV2; bp.NHU = pl.NHU;
+    for (int i = 0; i < 3; ++i) { bp.hu_blk[i] = pl.hu_blk[i]; bp.hu_pair0[i] = pl.hu_pair0[i]; }
+    bp.hu_splits[0] = pl.hu_splits[0]; bp.hu_splits[1] = pl.hu_splits[1];
     bp.enc = reinterpret_cast<const __nv_bfloat16*>(enc);
     bp.dec = reinterpret_cast<const __nv_bfloat16*>(dec);
     bp.NHC = (H + kDjChunkH - 1) / kDjChunkH;
@@ -183,9 +219,13 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
     e = cudaMemsetAsync(d_dec, 0, sizeof(float) * (size_t)B * U * H, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(d_dec)");
 
-    // dY operand images as a 2-D tensor [images * 128 rows, 64 v]: an un-swizzled box copies one image verbatim
-    CUtensorMap tmap_dy;
+    // operand images as 2-D tensors [images * 128 rows, 64]: an un-swizzled box copies image rows verbatim
+    CUtensorMap tmap_dy, tmap_dy_half, tmap_j_half;
     if (int rc = make_tmap_2d_bf16(&tmap_dy, jp.dY_img, (uint64_t)pl.chunk_tiles * pl.NT4 * 128, 64, 64, 128, CU_TENSOR_MAP_SWIZZLE_NONE))
+        return rc;
+    if (int rc = make_tmap_2d_bf16(&tmap_dy_half, jp.dY_img, (uint64_t)pl.chunk_tiles * pl.NT4 * 128, 64, 64, 64, CU_TENSOR_MAP_SWIZZLE_NONE))
+        return rc;
+    if (int rc = make_tmap_2d_bf16(&tmap_j_half, jp.J_img, (uint64_t)pl.chunk_tiles * jp.KB * 128, 64, 64, 64, CU_TENSOR_MAP_SWIZZLE_NONE))
         return rc;
 
     const DjSmem djL = dj_smem_layout();
@@ -255,14 +295,59 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
             timer.mark("dj_gemm");
         }
 
-        reduce_dpre_enc_kernel<<<sms * 8, 256, 0, st>>>(bp, d_enc);
-        reduce_dpre_dec_kernel<<<sms * 8, 256, 0, st>>>(bp, d_dec);
-        g_launches += 2;
-        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "reduce_dpre kernels launch");
-        timer.mark("reduce_dpre_enc+dec");
+        {
+            const int tT = 1 << jp.tT_log2;
+            const int g0 = t0 / jp.nTu, g1 = t1 / jp.nTu;
+            const int b0 = g0 / jp.nTt, b1 = (g1 - 1) / jp.nTt + 1;
+            const int rows = (g1 - g0) * tT + (b1 - b0) * U;
+            reduce_dpre_kernel<<<rows, 160, 0, st>>>(bp, d_enc, d_dec);
+            ++g_launches;
+            if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "reduce_dpre_kernel launch");
+            timer.mark("reduce_dpre");
+        }
 
         bp.accumulate = chunk_idx > 0;
-        dw_gemm_kernel<<<pl.NVT * pl.NHT * pl.n_splits, kBwdThreads, dwL.total, st>>>(bp);
+        {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(2 * pl.hu_pair0[pl.NHU]);
+            cfg.blockDim = dim3(kBwdThreads);
+            cfg.dynamicSmemBytes = dwL.total;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            static const bool prof_on = getenv("TSASR_DEBUG_PROF") != nullptr;
+            long long* d_prof = nullptr;
+            BwdParams bpp = bp;
+            const int n = 2 * pl.hu_pair0[pl.NHU];
+            if (prof_on) {
+                cudaMalloc(&d_prof, sizeof(long long) * 4 * n);
+                cudaMemset(d_prof, 0, sizeof(long long) * 4 * n);
+                bpp.prof = d_prof;
+            }
+            e = cudaLaunchKernelEx(&cfg, dw_gemm_kernel, tmap_dy_half, tmap_j_half, bpp);
+            if (prof_on) {
+                cudaStreamSynchronize(st);
+                long long* h = new long long[4 * n];
+                cudaMemcpy(h, d_prof, sizeof(long long) * 4 * n, cudaMemcpyDeviceToHost);
+                for (int u = 0; u < pl.NHU; ++u) {
+                    double tot = 0, full = 0, stages = 0;
+                    int nl = 0;
+                    for (int i = 0; i < n; ++i)
+                        if (h[4 * i] > 0 && h[4 * i + 1] == u) { tot += h[4 * i]; full += h[4 * i + 2]; stages += h[4 * i + 3]; ++nl; }
+                    if (nl) fprintf(stderr, "[tsasr prof] dw h-unit %d (blocks %d..%d, %d splits): pairs=%d cycles/pair=%.0f stages/pair=%.0f cycles/stage=%.0f wait full=%.1f%%\n",
+                                    u, pl.hu_blk[u], pl.hu_blk[u + 1], pl.hu_splits[u], nl, tot / nl, stages / nl, tot / stages, 100 * full / tot);
+                }
+                delete[] h;
+                cudaFree(d_prof);
+            }
+            if (e != cudaSuccess) return cuda_fail(e, "dw_gemm_kernel launch");
+        }
         ++g_launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "dw_gemm_kernel launch");
         timer.mark("dw_gemm");

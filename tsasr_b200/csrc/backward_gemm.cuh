@@ -46,11 +46,13 @@ struct BwdParams {
     float* dpre_part;  // [tile - tile_begin][tT + tU][H]
     int NHC;           // ceil(H / 256): chunks of h-rows per tile pair
     // dW
-    float* dW_part;    // [n_splits][NVT * 128][H]
-    float* db_part;    // [n_splits][NVT * 128]
-    int NVT;           // ceil(V / 128)
-    int NHT;           // h-tiles of up to 4 h-blocks
-    int n_splits;
+    float* dW_part;    // [max splits][NV2 * 256][H]
+    float* db_part;    // [max splits][NV2 * 256]
+    int NV2;           // ceil(V / 256): v-tiles of a CTA pair
+    int NHU;           // h-units (1 or 2); the last one also carries db
+    int hu_blk[3];     // unit u covers h-blocks [hu_blk[u], hu_blk[u+1])
+    int hu_splits[2];  // split-K factor of unit u
+    int hu_pair0[3];   // unit u is worked on by CTA pairs [hu_pair0[u], hu_pair0[u+1])
     int accumulate;    // 0: store, 1: read-modify-write (later chunks)
     long long* prof;   // development: MMA-warp cycle counters per CTA (or nullptr)
 };
@@ -320,174 +322,255 @@ dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     }
 }
 
-// Fold the per-tile partial rows (flat, h-contiguous, one thread per output element).  d_enc rows are
-// complete inside one (b, tt) group of label tiles (chunks are aligned to such groups) -> plain
-// stores.  d_dec rows accumulate over tt inside the chunk and, by read-modify-write, across chunks.
-__global__ void __launch_bounds__(256)
-reduce_dpre_enc_kernel(const BwdParams p, float* __restrict__ d_enc) {
+// Fold the per-tile partial rows: one block row per output row, one thread per 4 consecutive h (float4).
+// blockIdx.x < n_enc_rows: d_enc row (frame-tile group gl, ti) = sum over the live label tiles of the group --
+// rows are complete inside a chunk (chunks are aligned to whole (utterance, frame-tile) groups) -> plain stores.
+// Other blocks: d_dec row (b, u) = sum over the chunk's frame tiles of utterance b, accumulated across
+// chunks by read-modify-write (d_dec is zero-filled first).  Deterministic, no atomics.
+__global__ void __launch_bounds__(160)
+reduce_dpre_kernel(const BwdParams p, float* __restrict__ d_enc, float* __restrict__ d_dec) {
     const int tT = 1 << p.tT_log2, tU = kTileM >> p.tT_log2;
-    const int g_begin = p.tile_begin / p.nTu, n_groups = (p.tile_end - p.tile_begin) / p.nTu;
-    const long long total = (long long)n_groups * tT * p.H;
-    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
-        const int h = (int)(o % p.H);
-        const int ti = (int)((o / p.H) % tT);
-        const int gl = (int)(o / ((long long)p.H * tT));
+    const int g_begin = p.tile_begin / p.nTu, g_end = p.tile_end / p.nTu;
+    const int n_enc_rows = (g_end - g_begin) * tT;
+    const int H4 = p.H >> 2;
+    const size_t tile_stride4 = (size_t)(tT + tU) * H4;  // float4 units between consecutive tiles
+    const float4* part = reinterpret_cast<const float4*>(p.dpre_part);
+    if ((int)blockIdx.x < n_enc_rows) {
+        const int gl = blockIdx.x >> p.tT_log2, ti = blockIdx.x & (tT - 1);
         const int g = g_begin + gl;
         const int b = g / p.nTt, tt = g - b * p.nTt;
         const int t = tt * tT + ti;
-        if (t >= p.logit_lengths[b]) continue;  // rows beyond T_b stay zero (memset)
+        if (t >= p.logit_lengths[b]) return;  // rows beyond T_b stay zero (memset)
         const int n_tu = (p.target_lengths[b] + 1 + tU - 1) / tU;  // live label tiles
-        const float* base = p.dpre_part + ((size_t)gl * p.nTu * (tT + tU) + ti) * p.H + h;
-        float s = 0.f;
-        for (int tu = 0; tu < n_tu; ++tu) s += base[(size_t)tu * (tT + tU) * p.H];
-        d_enc[((size_t)b * p.T + t) * p.H + h] = s;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-reduce_dpre_dec_kernel(const BwdParams p, float* __restrict__ d_dec) {
-    const int tT = 1 << p.tT_log2, tU = kTileM >> p.tT_log2;
-    const int g_begin = p.tile_begin / p.nTu, g_end = p.tile_end / p.nTu;
-    const int b_begin = g_begin / p.nTt, b_end = (g_end - 1) / p.nTt + 1;
-    const long long total = (long long)(b_end - b_begin) * p.U * p.H;
-    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
-        const int h = (int)(o % p.H);
-        const int u = (int)((o / p.H) % p.U);
-        const int b = b_begin + (int)(o / ((long long)p.H * p.U));
-        const int Tb = p.logit_lengths[b];
-        if (u >= p.target_lengths[b] + 1) continue;
-        const int tu = u / tU, ui = u - tu * tU;
-        const int gb0 = max(g_begin, b * p.nTt), gb1 = min(g_end, (b + 1) * p.nTt);
-        float s = 0.f;
-        for (int g = gb0; g < gb1; ++g) {
-            if ((g - b * p.nTt) * tT >= Tb) break;  // dead frame tiles carry no data
-            s += p.dpre_part[((size_t)(g * p.nTu + tu - p.tile_begin) * (tT + tU) + tT + ui) * p.H + h];
+        for (int h4 = threadIdx.x; h4 < H4; h4 += blockDim.x) {
+            const float4* base = part + ((size_t)gl * p.nTu) * tile_stride4 + (size_t)ti * H4 + h4;
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int tu = 0; tu < n_tu; ++tu) {
+                const float4 x = base[(size_t)tu * tile_stride4];
+                s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+            }
+            reinterpret_cast<float4*>(d_enc)[((size_t)b * p.T + t) * H4 + h4] = s;
         }
-        d_dec[((size_t)b * p.U + u) * p.H + h] += s;
+    } else {
+        const int row = blockIdx.x - n_enc_rows;
+        const int b_begin = g_begin / p.nTt;
+        const int b = b_begin + row / p.U, u = row % p.U;
+        if (u >= p.target_lengths[b] + 1) return;
+        const int Tb = p.logit_lengths[b];
+        const int tu = u / tU, ui = u - tu * tU;
+        const int gb0 = max(g_begin, b * p.nTt), gb1 = min(min(g_end, (b + 1) * p.nTt), b * p.nTt + (Tb + tT - 1) / tT);
+        for (int h4 = threadIdx.x; h4 < H4; h4 += blockDim.x) {
+            const float4* base = part + ((size_t)(gb0 * p.nTu + tu - p.tile_begin)) * tile_stride4 + (size_t)(tT + ui) * H4 + h4;
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int g = gb0; g < gb1; ++g) {  // dead frame tiles carry no data
+                const float4 x = base[(size_t)(g - gb0) * p.nTu * tile_stride4];
+                s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+            }
+            float4* o = reinterpret_cast<float4*>(d_dec) + ((size_t)b * p.U + u) * H4 + h4;
+            float4 y = *o;
+            y.x += s.x; y.y += s.y; y.z += s.z; y.w += s.w;
+            *o = y;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// dW / db GEMM (contraction over cells), split-K over the chunk's tiles
+// dW / db GEMM (contraction over cells), split-K over the chunk's tiles, on CTA pairs
 // ------------------------------------------------------------------------------------------------
-static constexpr int kDwStages = 2;
-static constexpr int kDwStageBytes = 6 * kImgBytes;  // 2 dY v-block images + up to 4 J h-block images
+// dW[v, h] = sum_cells dY[cell, v] * J[cell, h] as a cta_group::2 MMA with M = 256 v-rows (each CTA owns 128 =
+// two dY images, MN-major A) and N = up to 512 h-columns (the pair's whole TMEM width; each CTA supplies half
+// of the J images, MN-major B).  The accumulator lives in TMEM for the whole kernel (split-K over the tiles of
+// the chunk); a unit is (256 v-rows, h-unit, split).  H is cut into at most two h-units so that the last one
+// leaves room for db: 32 extra accumulator columns fed by a constant "ones" block (db[v] = sum_cells dY[cell, v]).
+// A pipeline stage is HALF a cell tile (64 cells: 8 KB half-images); the ring holds as many stages as fit
+// 192 KB (4 for a 512-column unit, 8 for a 128-column unit: the narrow units need the depth to cover L2 latency).
+static constexpr int kDwMaxStages = 8;
+static constexpr int kDwHalfImg = kImgBytes / 2;          // rows 0-63 or 64-127 of an operand image
+static constexpr int kDwRingBytes = 24 * kDwHalfImg;      // 192 KB
+static constexpr int kDwDbCols = 32;
 
 struct DwSmem { uint32_t stage_off, ones_off, bar_off, tmem_off, total; };
 __host__ __device__ inline DwSmem dw_smem_layout() {
     DwSmem l;
     l.stage_off = 0;
-    l.ones_off = kDwStages * kDwStageBytes;
-    l.bar_off = l.ones_off + kImgBytes;
-    l.tmem_off = l.bar_off + 8 * 8;
+    l.ones_off = kDwRingBytes;
+    l.bar_off = l.ones_off + kDwHalfImg;
+    l.tmem_off = l.bar_off + 24 * 8;
     l.total = l.tmem_off + 16;
     return l;
 }
 
+// One pipeline stage of the dW kernel in ONE asm statement: four K = 16 steps (all descriptors advance by 16
+// rows = 2048 B), each with up to three MMAs sharing the A operand: dW columns [0,256) (idesc0), dW columns
+// [256,512) from the J blocks two half-images further (idesc1, if has1) and the db columns fed by the constant
+// ones block (idesc_db, if has_db).  Issued by a converged warp, one lane elected once.
+__device__ __forceinline__ void umma_dw_stage_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint64_t o_desc, uint32_t idesc0,
+                                                uint32_t idesc1, uint32_t idesc_db, uint32_t accumulate_first, uint32_t has1,
+                                                uint32_t has_db, uint32_t db_col) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t, h1, hd;\n\t"
+        ".reg .b64 a1, a2, a3, b1, b2, b3, c0, c1, c2, c3, o1, o2, o3;\n\t.reg .b32 d1, dd;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "setp.ne.b32 h1, %8, 0;\n\tand.pred h1, h1, q;\n\t"
+        "setp.ne.b32 hd, %9, 0;\n\tand.pred hd, hd, q;\n\t"
+        "add.u32 d1, %0, 256;\n\tadd.u32 dd, %0, %10;\n\t"
+        "add.u64 a1, %1, 128;\n\tadd.u64 a2, %1, 256;\n\tadd.u64 a3, %1, 384;\n\t"
+        "add.u64 b1, %2, 128;\n\tadd.u64 b2, %2, 256;\n\tadd.u64 b3, %2, 384;\n\t"
+        "add.u64 c0, %2, 1024;\n\tadd.u64 c1, %2, 1152;\n\tadd.u64 c2, %2, 1280;\n\tadd.u64 c3, %2, 1408;\n\t"
+        "add.u64 o1, %3, 128;\n\tadd.u64 o2, %3, 256;\n\tadd.u64 o3, %3, 384;\n\t"
+        "@q  tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %4, p;\n\t"
+        "@h1 tcgen05.mma.cta_group::2.kind::f16 [d1], %1, c0, %5, p;\n\t"
+        "@hd tcgen05.mma.cta_group::2.kind::f16 [dd], %1, %3, %6, p;\n\t"
+        "@q  tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %4, t;\n\t"
+        "@h1 tcgen05.mma.cta_group::2.kind::f16 [d1], a1, c1, %5, t;\n\t"
+        "@hd tcgen05.mma.cta_group::2.kind::f16 [dd], a1, o1, %6, t;\n\t"
+        "@q  tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %4, t;\n\t"
+        "@h1 tcgen05.mma.cta_group::2.kind::f16 [d1], a2, c2, %5, t;\n\t"
+        "@hd tcgen05.mma.cta_group::2.kind::f16 [dd], a2, o2, %6, t;\n\t"
+        "@q  tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %4, t;\n\t"
+        "@h1 tcgen05.mma.cta_group::2.kind::f16 [d1], a3, c3, %5, t;\n\t"
+        "@hd tcgen05.mma.cta_group::2.kind::f16 [dd], a3, o3, %6, t;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "l"(o_desc), "r"(idesc0), "r"(idesc1), "r"(idesc_db), "r"(accumulate_first),
+          "r"(has1), "r"(has_db), "r"(db_col) : "memory");
+}
+
 __global__ void __launch_bounds__(kBwdThreads, 1)
-dw_gemm_kernel(const BwdParams p) {
+dw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_j, const BwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const DwSmem L = dw_smem_layout();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
-    uint64_t* full = bars;        // [2]
-    uint64_t* empty = bars + 2;   // [2]
-    uint64_t* acc_full = bars + 4;
+    uint64_t* full = bars;        // [n_stages]  leader: bytes of both CTAs
+    uint64_t* empty = bars + 8;   // [n_stages]  every CTA
+    uint64_t* acc_full = bars + 16;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
 
-    // unit = (v-tile, h-tile, split)
-    const int unit = blockIdx.x;
-    const int split = unit % p.n_splits;
-    const int ht = (unit / p.n_splits) % p.NHT;
-    const int vt = unit / (p.n_splits * p.NHT);
-    const int hb0 = ht * 4, nhb = min(4, p.KB - hb0);
-    const int nvb = min(2, p.NVB - vt * 2);          // v-block images that exist for this v-tile
-    const bool with_db = ht == p.NHT - 1;            // the last h-tile also carries the bias gradient
+    // unit = (v-tile of 256 rows, h-unit, split)
+    const int pair = (int)cluster_id_x();
+    const int hu = (p.NHU > 1 && pair >= p.hu_pair0[1]) ? 1 : 0;
+    const int local = pair - p.hu_pair0[hu];
+    const int n_splits = p.hu_splits[hu];
+    const int split = local % n_splits, vt2 = local / n_splits;
+    const int hb0 = p.hu_blk[hu];
+    const int nblk = p.hu_blk[hu + 1] - hb0;      // real h-blocks of the unit
+    const int nblk_e = (nblk + 1) & ~1;           // even: the pair's CTAs supply equal halves
+    const int nb0 = min(4, nblk_e), nb1 = nblk_e - nb0;  // blocks per MMA (N = 64 * nb)
+    const bool with_db = hu == p.NHU - 1;
     const int n_tiles = p.tile_end - p.tile_begin;
+    const int n_slots = (nb0 >> 1) + (nb1 >> 1);  // J half-images per CTA and stage
+    const uint32_t stage_bytes = (uint32_t)(2 + n_slots) * kDwHalfImg;
+    const uint32_t n_stages = min((uint32_t)kDwMaxStages, kDwRingBytes / stage_bytes);
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();
-        for (int i = 0; i < kDwStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (uint32_t i = 0; i < n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
-    // constant "ones" B block: J-image layout with column h = 0 set to 1.0 for all 128 cells
+    // constant "ones" B block (leader: column 0 = 1.0 for all 64 cells; partner: zeros)
     {
         uint4* o = reinterpret_cast<uint4*>(smem + L.ones_off);
-        for (int i = threadIdx.x; i < kImgBytes / 16; i += blockDim.x) o[i] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < kDwHalfImg / 16; i += blockDim.x) o[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
-        if (threadIdx.x < 128)
+        if (rank == 0 && threadIdx.x < 64)
             *reinterpret_cast<uint16_t*>(smem + L.ones_off + sw128_offset(threadIdx.x, 0)) = 0x3F80;  // bf16 1.0
         fence_proxy_async_smem();
     }
-    if (warp_idx == kBwdWarpMma) tmem_alloc<512>(tmem_ptr);
+    if (warp_idx == kBwdWarpLoad && lane == 0) { tma_prefetch_desc(&tmap_dy); tma_prefetch_desc(&tmap_j); }
+    if (warp_idx == kBwdWarpMma) tmem_alloc_2cta<512>(tmem_ptr);
     tcgen05_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
+    // J h-block held in shared slot j (= 2 * mma + i) of CTA r: D columns come out in natural h order
+    auto slot_block = [&](int r, int j) -> int {
+        const int m = j >> 1, i = j & 1;
+        const int nb = m ? nb1 : nb0;
+        if (i >= (nb >> 1)) return -1;
+        const int hb = hb0 + 4 * m + r * (nb >> 1) + i;
+        return hb < p.KB ? hb : -1;
+    };
+
     if (warp_idx == kBwdWarpLoad) {
-        {
-            uint32_t stage = 0, phase = 0;
-            for (int tl = split; tl < n_tiles; tl += p.n_splits) {
-                if (!tile_live(p, p.tile_begin + tl)) continue;
+        uint32_t stage = 0, phase = 0;
+        const uint32_t full0 = mapa_u32(smem_u32(&full[0]), 0);
+        int nB[2] = {0, 0};
+        for (int r = 0; r < 2; ++r)
+            for (int j = 0; j < 4; ++j) nB[r] += slot_block(r, j) >= 0;
+        const uint32_t bytes_pair = (uint32_t)(4 + nB[0] + nB[1]) * kDwHalfImg;
+        for (int tl = split; tl < n_tiles; tl += n_splits) {
+            if (!tile_live(p, p.tile_begin + tl)) continue;
+            const int dy_row0 = (tl * p.NT4 + vt2 * 4 + rank * 2) * 128;
+            for (int half = 0; half < 2; ++half) {
                 mbar_wait(&empty[stage], phase ^ 1, 0xB00 | stage);
                 __syncwarp();
-                uint8_t* st = smem + L.stage_off + stage * kDwStageBytes;
-                const uint8_t* dy = reinterpret_cast<const uint8_t*>(p.dY_img) + ((size_t)tl * p.NT4 + vt * 2) * kImgBytes;
-                const uint8_t* jm = reinterpret_cast<const uint8_t*>(p.J_img) + ((size_t)tl * p.KB + hb0) * kImgBytes;
-                mbar_arrive_expect_tx_e(&full[stage], (2 + nhb) * kImgBytes);
-                bulk_load_1d_e(st, dy, kImgBytes, &full[stage]);
-                // a v-tile whose second 64-column block lies beyond V re-reads the first block: those
-                // accumulator rows (v >= V) are never stored
-                bulk_load_1d_e(st + kImgBytes, dy + (nvb == 2 ? kImgBytes : 0), kImgBytes, &full[stage]);
-                bulk_load_1d_e(st + 2 * kImgBytes, jm, nhb * kImgBytes, &full[stage]);
-                if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+                uint8_t* st = smem + L.stage_off + stage * stage_bytes;
+                if (rank == 0) mbar_arrive_expect_tx_e(&full[stage], bytes_pair);
+                tma_load_2d_2cta_e(st, &tmap_dy, full0 + stage * 8, 0, dy_row0 + half * 64);
+                tma_load_2d_2cta_e(st + kDwHalfImg, &tmap_dy, full0 + stage * 8, 0, dy_row0 + 128 + half * 64);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int hb = slot_block(rank, j);
+                    if (hb >= 0) tma_load_2d_2cta_e(st + (2 + j) * kDwHalfImg, &tmap_j, full0 + stage * 8, 0, (tl * p.KB + hb) * 128 + half * 64);
+                }
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp_idx == kBwdWarpMma) {
-        {  // whole warp, converged
+        if (rank == 0) {  // whole warp, converged
             uint32_t stage = 0, phase = 0;
             bool first = true;
-            const uint32_t idesc = make_idesc_bf16(kTileM, nhb * 64, 1, 1);
-            const uint32_t idesc_db = make_idesc_bf16(kTileM, 16, 1, 1);
-            const uint32_t ones_base = smem_u32(smem + L.ones_off);
-            for (int tl = split; tl < n_tiles; tl += p.n_splits) {
+            const uint32_t idesc0 = make_idesc_bf16(256, nb0 * 64, 1, 1);
+            const uint32_t idesc1 = make_idesc_bf16(256, nb1 > 0 ? nb1 * 64 : 64, 1, 1);
+            const uint32_t idesc_db = make_idesc_bf16(256, kDwDbCols, 1, 1);
+            // MN-major operands: 64-wide blocks kDwHalfImg apart, 8-row K groups 1024 B apart; a k-step is 16 rows
+            const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smem + L.stage_off), kDwHalfImg, 1024);
+            const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem + L.stage_off) + 2 * kDwHalfImg, kDwHalfImg, 1024);
+            const uint64_t o_desc0 = make_smem_desc_sw128(smem_u32(smem + L.ones_off), kDwHalfImg, 1024);
+            long long t_full = 0, tm = 0, n_st = 0;
+            const long long t_begin = clock64();
+            for (int tl = split; tl < n_tiles; tl += n_splits) {
                 if (!tile_live(p, p.tile_begin + tl)) continue;
-                mbar_wait(&full[stage], phase, 0xC00 | stage);
-                tcgen05_fence_after();
-                const uint32_t a_base = smem_u32(smem + L.stage_off + stage * kDwStageBytes);
-                const uint32_t b_base = a_base + 2 * kImgBytes;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {  // 16 cells per step = two 8-row groups of the image
-                    const uint64_t a_desc = make_smem_desc_sw128(a_base + k * 2048, kImgBytes, 1024);  // MN-major, M = v
-                    const uint64_t b_desc = make_smem_desc_sw128(b_base + k * 2048, kImgBytes, 1024);  // MN-major, N = h
-                    umma_bf16_e(tmem_base, a_desc, b_desc, idesc, !(first && k == 0));
-                    if (with_db) {
-                        const uint64_t o_desc = make_smem_desc_sw128(ones_base + k * 2048, kImgBytes, 1024);
-                        umma_bf16_e(tmem_base + 256, a_desc, o_desc, idesc_db, !(first && k == 0));
-                    }
+                for (int half = 0; half < 2; ++half) {
+                    if (p.prof) tm = clock64();
+                    mbar_wait(&full[stage], phase, 0xC00 | stage);
+                    if (p.prof) { t_full += clock64() - tm; ++n_st; }
+                    tcgen05_fence_after();
+                    // 4 k-steps x (dW columns 0-255, dW columns 256-511, db) in one issue block
+                    const uint32_t off = stage * (stage_bytes >> 4);
+                    umma_dw_stage_e(tmem_base, a_desc0 + off, b_desc0 + off, o_desc0, idesc0, idesc1, idesc_db, !first,
+                                    nb1 > 0, with_db, nblk_e * 64);
+                    first = false;
+                    umma_commit_2cta_e(&empty[stage], 3);
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
-                first = false;
-                umma_commit_e(&empty[stage]);
-                if (++stage == kDwStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit_e(acc_full);
+            umma_commit_2cta_e(acc_full, 3);
+            if (p.prof && lane == 0) {
+                long long* o = p.prof + blockIdx.x * 4;
+                o[0] = clock64() - t_begin; o[1] = hu; o[2] = t_full; o[3] = n_st;
+            }
         }
     } else {
         const int q = warp_idx & 3;
         const int row = q * 32 + lane;
-        const int v = vt * 128 + row;
+        const int v = vt2 * 256 + rank * 128 + row;
         // did this split see any live tile?  (all roles agree; the epilogue must not wait otherwise)
         bool any = false;
-        for (int tl = split; tl < n_tiles; tl += p.n_splits) any |= tile_live(p, p.tile_begin + tl);
-        const size_t vrows = (size_t)p.NVT * 128;
+        for (int tl = split; tl < n_tiles; tl += n_splits) any |= tile_live(p, p.tile_begin + tl);
+        const size_t vrows = (size_t)p.NV2 * 256;
         float* wrow = p.dW_part + ((size_t)split * vrows + v) * p.H + hb0 * 64;
         if (any) {
             mbar_wait(acc_full, 0, 0xD00);
             tcgen05_fence_after();
         }
-        for (int cc = 0; cc < nhb * 64; cc += 32) {
+        for (int cc = 0; cc < nblk * 64; cc += 32) {
             uint32_t raw[32];
             if (any) {
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + cc, raw);
@@ -509,10 +592,10 @@ dw_gemm_kernel(const BwdParams p) {
             }
         }
         if (with_db) {
-            uint32_t raw[32];
+            uint32_t raw[16];
             float x = 0.f;
             if (any) {
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + 256, raw);
+                tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + nblk_e * 64, raw);
                 tmem_ld_wait();
                 x = __uint_as_float(raw[0]);
             }
@@ -521,24 +604,27 @@ dw_gemm_kernel(const BwdParams p) {
         }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     if (warp_idx == kBwdWarpMma) {
         tcgen05_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        tmem_dealloc_2cta<512>(tmem_base);
     }
 }
 
 __global__ void reduce_dw_kernel(const BwdParams p, float* __restrict__ dW, float* __restrict__ db) {
-    const size_t vrows = (size_t)p.NVT * 128;
+    const size_t vrows = (size_t)p.NV2 * 256;
     const size_t n = (size_t)p.V * p.H;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int h = (int)(i % p.H);
+        const int ns = p.hu_splits[(p.NHU > 1 && h >= p.hu_blk[1] * 64) ? 1 : 0];
         float s = 0.f;
-        for (int sp = 0; sp < p.n_splits; ++sp) s += p.dW_part[(size_t)sp * vrows * p.H + i];
+        for (int sp = 0; sp < ns; ++sp) s += p.dW_part[(size_t)sp * vrows * p.H + i];
         dW[i] = s;
     }
+    const int ns_db = p.hu_splits[p.NHU - 1];
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < (size_t)p.V; v += (size_t)gridDim.x * blockDim.x) {
         float s = 0.f;
-        for (int sp = 0; sp < p.n_splits; ++sp) s += p.db_part[(size_t)sp * vrows + v];
+        for (int sp = 0; sp < ns_db; ++sp) s += p.db_part[(size_t)sp * vrows + v];
         db[v] = s;
     }
 }
