@@ -60,7 +60,8 @@ static constexpr int kFirstEpilogueWarp = 0;   // warps 0-7  (TMEM lane quarter 
 static constexpr int kFirstProducerWarp = 8;   // warps 8-15
 static constexpr int kWarpTmaW = 16;
 static constexpr int kWarpTmaSlices = 17;
-static constexpr int kWarpMma = 19;
+static constexpr int kWarpRelayA = 18;    // partner CTA of a pair only
+static constexpr int kWarpMma = 19;       // leader: MMA issue; partner: accumulator-release relay
 static constexpr float kLog2eF = 1.4426950408889634f;
 static constexpr float kLn2F = 0.6931471805599453f;
 
@@ -154,8 +155,9 @@ __host__ __device__ inline SmemLayout smem_layout(int KB, int num_w_stages) {
     l.bias_off = l.slice_off + kSliceRingBytes;
     l.xchg_off = l.bias_off + 2 * kTileN * 4;
     l.bar_off = l.xchg_off + 2 * kTileM * 16;
-    // barriers: w_full[3] w_empty[3] s_full[3] s_empty[3] a_full[10] a_empty[10] acc_full[2] acc_empty[2] = 36
-    l.tmem_off = l.bar_off + 40 * 8;
+    // barriers: w_full[3] w_empty[3] s_full[3] s_empty[3] a_full[10] a_empty[10] acc_full[2] acc_empty[2] = 36,
+    // a_done[10] acc_done[2] (partner CTA only: local collection points relayed to the leader) = 48
+    l.tmem_off = l.bar_off + 48 * 8;
     l.total = l.tmem_off + 16;
     return l;
 }
@@ -174,7 +176,9 @@ template <int MODE, int ACT, bool PAIR>
 __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a, const uint8_t* slices,
                                           uint64_t* s_full, uint64_t* s_empty, uint64_t* a_full, uint64_t* a_empty) {
     const Rounds<PAIR> rounds(p);
-    const bool remote = PAIR && rounds.rank != 0;  // a_full lives in the leader CTA
+    // The partner CTA's producers arrive on a LOCAL barrier (a_full points at a_done there); a relay warp
+    // forwards it to the leader.  A remote arrive has cluster-scope release semantics (MEMBAR.GPU), which in
+    // MODE_GRAD would make every producer warp wait for its J-image global stores to drain.
     const int lane = threadIdx.x & 31;
     const int ptid = threadIdx.x - kFirstProducerWarp * 32;  // 0..255
     const int c = ptid & 7;                                  // 16-byte chunk inside the 128-byte row
@@ -199,7 +203,7 @@ __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a,
             for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(&a_empty[kb], (it & 1) ^ 1, 0x540 | kb);
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&a_full[kb]), 0));
+                if (lane == 0) mbar_arrive(&a_full[kb]);
             }
             ++it;
             continue;
@@ -253,10 +257,7 @@ __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a,
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                if (remote) mbar_arrive_cluster(mapa_u32(smem_u32(&a_full[kb]), 0));
-                else mbar_arrive(&a_full[kb]);
-            }
+            if (lane == 0) mbar_arrive(&a_full[kb]);
         }
         ++it;
     }
@@ -282,6 +283,8 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     uint64_t* a_empty = bars + 22;
     uint64_t* acc_full = bars + 32;
     uint64_t* acc_empty = bars + 34;
+    uint64_t* a_done = bars + 36;
+    uint64_t* acc_done = bars + 46;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
 
     const int warp_idx = threadIdx.x >> 5;
@@ -296,8 +299,9 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         // barriers the MMA lane waits on live in the leader CTA and collect arrivals from both CTAs
         for (int i = 0; i < NS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         for (int i = 0; i < NSL; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kNumProducerWarps); }
-        for (int i = 0; i < KB; ++i) { mbar_init(&a_full[i], kNumProducerWarps * kCtas); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kNumEpilogueWarps * kCtas); }
+        // a_full / acc_empty (leader): its own 8 warps + one relayed arrival for the partner's 8 warps
+        for (int i = 0; i < KB; ++i) { mbar_init(&a_full[i], kNumProducerWarps + (PAIR ? 1 : 0)); mbar_init(&a_empty[i], 1); mbar_init(&a_done[i], kNumProducerWarps); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kNumEpilogueWarps + (PAIR ? 1 : 0)); mbar_init(&acc_done[i], kNumEpilogueWarps); }
         fence_barrier_init();
     }
     if (warp_idx == kWarpTmaW && lane == 0) tma_prefetch_desc(&tmap_w);
@@ -428,6 +432,38 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 long long* o = p.prof + blockIdx.x * 8;
                 o[0] = clock64() - t_begin; o[1] = t_acc; o[2] = t_a; o[3] = t_w; o[4] = it; o[5] = l_sum; o[6] = l_cnt; o[7] = t_commit[0];
             }
+        } else if (PAIR) {
+            // partner CTA: relay "all 8 epilogue warps released accumulator buffer b" to the leader's acc_empty
+            const uint32_t acc_empty_leader = mapa_u32(smem_u32(&acc_empty[0]), 0);
+            uint32_t acc_it = 0;
+            for (int t0 = rounds.first; t0 < p.tile_end; t0 += rounds.step) {
+                int tile;
+                TileCoord tc;
+                if (!rounds.open(p, t0, tile, tc)) continue;
+                for (int nt = 0; nt < NT; ++nt, ++acc_it) {
+                    const uint32_t buf = acc_it & 1;
+                    mbar_wait(&acc_done[buf], (acc_it >> 1) & 1, 0x280 | buf);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(acc_empty_leader + buf * 8);
+                }
+            }
+        }
+    } else if (PAIR && warp_idx == kWarpRelayA) {
+        // partner CTA: relay "all 8 producer warps wrote A block kb" to the leader's a_full
+        if (!leader) {
+            const uint32_t a_full_leader = mapa_u32(smem_u32(&a_full[0]), 0);
+            uint32_t it = 0;
+            for (int t0 = rounds.first; t0 < p.tile_end; t0 += rounds.step) {
+                int tile;
+                TileCoord tc;
+                if (!rounds.open(p, t0, tile, tc)) continue;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&a_done[kb], it & 1, 0x380 | kb);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(a_full_leader + kb * 8);
+                }
+                ++it;
+            }
         }
     } else if (warp_idx == kWarpTmaSlices) {
         // ===================== enc / dec slice producer (TMA) =====================
@@ -452,11 +488,12 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         }
     } else if (warp_idx >= kFirstProducerWarp && warp_idx < kFirstProducerWarp + kNumProducerWarps) {
         // ===================== A producers: J = bf16(act(enc + dec)) =====================
+        uint64_t* a_arrive = (PAIR && !leader) ? a_done : a_full;
         switch (p.act_kind) {
-            case ACT_LEAKY_RELU: produce_a<MODE, ACT_LEAKY_RELU, PAIR>(p, smem_a, slices, s_full, s_empty, a_full, a_empty); break;
-            case ACT_RELU: produce_a<MODE, ACT_RELU, PAIR>(p, smem_a, slices, s_full, s_empty, a_full, a_empty); break;
-            case ACT_TANH: produce_a<MODE, ACT_TANH, PAIR>(p, smem_a, slices, s_full, s_empty, a_full, a_empty); break;
-            default: produce_a<MODE, ACT_IDENTITY, PAIR>(p, smem_a, slices, s_full, s_empty, a_full, a_empty); break;
+            case ACT_LEAKY_RELU: produce_a<MODE, ACT_LEAKY_RELU, PAIR>(p, smem_a, slices, s_full, s_empty, a_arrive, a_empty); break;
+            case ACT_RELU: produce_a<MODE, ACT_RELU, PAIR>(p, smem_a, slices, s_full, s_empty, a_arrive, a_empty); break;
+            case ACT_TANH: produce_a<MODE, ACT_TANH, PAIR>(p, smem_a, slices, s_full, s_empty, a_arrive, a_empty); break;
+            default: produce_a<MODE, ACT_IDENTITY, PAIR>(p, smem_a, slices, s_full, s_empty, a_arrive, a_empty); break;
         }
     } else if (warp_idx < kFirstEpilogueWarp + kNumEpilogueWarps) {
         // ===================== epilogue =====================
@@ -472,7 +509,8 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         uint32_t acc_it = 0, it = 0;
         float nb0 = 0.f;  // prefetched bias value of the next vocabulary tile
         int nb_nt = -1;
-        const uint32_t acc_empty_leader0 = PAIR ? mapa_u32(smem_u32(&acc_empty[0]), 0) : 0u;
+        // the partner CTA releases accumulators on a local barrier that its relay warp forwards to the leader
+        uint64_t* acc_release = (PAIR && !leader) ? acc_done : acc_empty;
         for (int t0 = rounds.first; t0 < p.tile_end; t0 += rounds.step) {
             int tile;
             TileCoord tc;
@@ -484,7 +522,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                     tcgen05_fence_after();
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(acc_empty_leader0 + buf * 8);
+                    if (lane == 0) mbar_arrive(&acc_release[buf]);
                 }
                 if (MODE == MODE_FWD) asm volatile("bar.sync 3, 256;" ::: "memory");
                 ++it;
@@ -681,10 +719,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 }
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) {
-                    if (PAIR && !leader) mbar_arrive_cluster(acc_empty_leader0 + buf * 8);
-                    else mbar_arrive(&acc_empty[buf]);
-                }
+                if (lane == 0) mbar_arrive(&acc_release[buf]);
             }
             if (MODE == MODE_FWD) {
                 // merge the two groups' running (max, sum) and picked logits; group 0 writes the lattice
