@@ -112,14 +112,6 @@ __device__ __forceinline__ void umma_bf16_2cta_x4_mnA_e(uint32_t d_tmem, uint64_
         "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, t;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_2cta_e(void* smem_dst, const void* tmap, uint32_t mbar_cluster, int x, int y) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\t"
-        "elect.sync _|q, 0xffffffff;\n\t"
-        "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
-        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(mbar_cluster), "r"(x), "r"(y) : "memory");
-}
-
 // act'(x) of the pre-activation x = enc + dec, evaluated exactly as the forward does it: the derivative is
 // taken at the bf16-rounded activation output (sign for (leaky) ReLU, 1 - J^2 for tanh).
 template <int ACT>

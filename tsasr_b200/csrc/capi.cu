@@ -166,11 +166,14 @@ static int fill_joint_params(JointParams& p, const void* enc, const void* dec, c
     if ((int)smem_layout(p.KB, ns).total > max_smem)
         return fail(TSASR_E_UNSUPPORTED, "not enough shared memory (%d B) for H=%d", max_smem, H);
     p.num_w_stages = ns;
-    p.num_slice_slots = kSliceRingBytes / ((tT + tU) * 128);
+    static const int dbg_skip = getenv("TSASR_DEBUG_SKIP") ? atoi(getenv("TSASR_DEBUG_SKIP")) : 0;
+    p.dbg_skip = dbg_skip;
+    p.enc = reinterpret_cast<const __nv_bfloat16*>(enc);
+    p.dec = reinterpret_cast<const __nv_bfloat16*>(dec);
     return TSASR_OK;
 }
 
-struct JointMaps { CUtensorMap w, enc, dec; };
+struct JointMaps { CUtensorMap w; };
 
 // W [V,H]: 64-byte swizzled k-slices of 256 rows; enc [B*T,H] / dec [B*U,H]: plain [rows x 64] slices
 static int make_joint_maps(JointMaps* m, const JointParams& p, const void* enc, const void* dec, const void* W) {
@@ -180,8 +183,6 @@ static int make_joint_maps(JointMaps* m, const JointParams& p, const void* enc, 
     } else {
         if (int rc = make_tmap_2d_bf16(&m->w, W, (uint64_t)p.V, (uint64_t)p.H, kWStageK, kTileN, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
     }
-    if (int rc = make_tmap_2d_bf16(&m->enc, enc, (uint64_t)p.B * p.T, (uint64_t)p.H, kABlockK, tT, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
-    if (int rc = make_tmap_2d_bf16(&m->dec, dec, (uint64_t)p.B * p.U, (uint64_t)p.H, kABlockK, tU, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
     return TSASR_OK;
 }
 
@@ -221,7 +222,7 @@ static int launch_joint_impl(const JointMaps& maps, const JointParams& p, int nu
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, maps.w, maps.enc, maps.dec, pp);
+    e = cudaLaunchKernelEx(&cfg, kern, maps.w, pp);
     ++g_launches;
     if (e != cudaSuccess) return cuda_fail(e, "joint_gemm_kernel launch");
     e = cudaGetLastError();

@@ -342,6 +342,14 @@ __device__ __forceinline__ void tma_load_2d_2cta_mcast_e(void* smem_dst, const v
         " [%0], [%1, {%4, %5}], [%2], %3;\n\t}"
         ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(mbar_local) & 0xFEFFFFFFu), "h"(cta_mask), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_2cta_e(void* smem_dst, const void* tmap, uint32_t mbar_cluster, int x, int y) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(mbar_cluster), "r"(x), "r"(y) : "memory");
+}
+
 __device__ __forceinline__ void bulk_load_1d_e(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .pred q;\n\t"

@@ -7,20 +7,26 @@
 // ever writing J ([B,T,U,H]) or the logits ([B,T,U,V]) to HBM.
 //
 // One persistent CTA per SM, 20 warps (640 threads):
-//   warp 16      TMA producer: streams W k-slices through a 3-stage ring
+//   warp 16      TMA producer: streams W k-slices through a 3- or 4-stage ring (what fits beside the A operand)
 //   warp 19      allocates TMEM, then ONE lane issues tcgen05.mma (N<=256, K=16, bf16 -> fp32); highest warp id
-//                = highest issue priority, because this lane is the serial resource of the kernel
-//   warp 17      TMA producer: stages the enc [tT x 64] and dec [tU x 64] bf16 slices of the current
-//                k-block in a small shared-memory ring (so the A producers never wait on L2)
+//                = highest issue priority, because this lane is the serial resource of the kernel.
+//                (pair partner: relays "accumulator released" from its epilogue warps to the leader)
+//   warp 18      pair partner only: relays "A block written" from its producer warps to the leader
 //   warps 8-15   A producers: build the 128-cell x H operand in shared memory in the canonical
-//                K-major SWIZZLE_128B layout (broadcast add + activation + bf16 round fused here);
+//                K-major SWIZZLE_128B layout (broadcast add + activation + bf16 round fused here) from enc/dec
+//                rows read straight from global memory (L1/L2 resident), one k-block prefetched ahead;
 //                the operand stays resident for all N tiles of the cell tile
-//   warps 0-7    epilogue, two groups of four warps; group g owns accumulator buffer g (2 x 256 TMEM
-//                columns), so vocabulary tiles alternate between the groups.  MODE_FWD: online
+//   warps 0-7    epilogue, two groups of four warps; both groups work on every accumulator buffer (2 x 256 TMEM
+//                columns), group g on columns [128 g, 128 g + 128).  MODE_FWD: online
 //                log-softmax keeping {lp_blank, lp_emit, logZ} (the groups merge their running
 //                (max, sum) through shared memory at the end of a cell tile); MODE_GRAD: recompute the
 //                softmax and emit bf16 dlogits tiles as pre-swizzled operand images for the backward
 //                GEMMs; MODE_DEBUG: dump raw logits (tests only).
+//
+// Measured ceiling (TSASR_DEBUG_SKIP ablations, B200, config 2): with epilogue, producers and W stream all
+// disabled a pair round takes 22.7k cycles (20.5k = 160 MMAs x 128); each of the three adds 3.5-5k cycles on
+// its own and the sum is ~additive (36k).  K = H = 640 means an accumulator is drained from TMEM every 10
+// pipeline stages, and TMEM drains, operand writes and the MMA's own operand reads contend inside the SM.
 //
 // PAIR = true runs the same roles on CTA pairs (2-CTA clusters, tcgen05 cta_group::2): the pair works on two
 // cell tiles at once with ONE M=256 MMA stream issued by the leader CTA; each CTA keeps its own A operand,
@@ -49,8 +55,7 @@ static constexpr int kWStageK = 32;
 static constexpr int kWStageKPair = 64;
 static constexpr int kWStageBytes = kTileN * kWStageK * 2;  // 16 KB
 static constexpr int kMaxKB = 10;         // H <= 640
-static constexpr int kMaxWStages = 3;
-static constexpr int kSliceRingBytes = 9216;  // enc/dec slice ring: 3 slots of 24 rows or 2 slots of 36 rows
+static constexpr int kMaxWStages = 4;
 static constexpr int kNumThreads = 640;
 static constexpr int kNumProducerWarps = 8;
 static constexpr int kNumEpilogueWarps = 8;
@@ -59,7 +64,6 @@ static constexpr int kNumEpilogueWarps = 8;
 static constexpr int kFirstEpilogueWarp = 0;   // warps 0-7  (TMEM lane quarter = warp & 3)
 static constexpr int kFirstProducerWarp = 8;   // warps 8-15
 static constexpr int kWarpTmaW = 16;
-static constexpr int kWarpTmaSlices = 17;
 static constexpr int kWarpRelayA = 18;    // partner CTA of a pair only
 static constexpr int kWarpMma = 19;       // leader: MMA issue; partner: accumulator-release relay
 static constexpr float kLog2eF = 1.4426950408889634f;
@@ -82,7 +86,9 @@ struct JointParams {
     int NT;                     // ceil(V / 256)
     int n_last;                 // UMMA N of the last vocabulary tile (multiple of 16)
     int num_w_stages;
-    int num_slice_slots;
+    int dbg_skip;               // development ablations: 1 = epilogue only releases, 2 = producers only arrive, 4 = no W stream
+    const __nv_bfloat16* enc;   // [B,T,H]
+    const __nv_bfloat16* dec;   // [B,U,H]
     // MODE_FWD outputs (skewed lattice layout)
     float2* lat2;
     float* logz;
@@ -145,17 +151,16 @@ struct Rounds {
 
 // shared memory carve-up (dynamic; base must be 1024-byte aligned)
 struct SmemLayout {
-    uint32_t a_off, w_off, slice_off, bias_off, xchg_off, bar_off, tmem_off, total;
+    uint32_t a_off, w_off, bias_off, xchg_off, bar_off, tmem_off, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int KB, int num_w_stages) {
     SmemLayout l;
     l.a_off = 0;
     l.w_off = l.a_off + (uint32_t)KB * kABlockBytes;
-    l.slice_off = l.w_off + (uint32_t)num_w_stages * kWStageBytes;
-    l.bias_off = l.slice_off + kSliceRingBytes;
+    l.bias_off = l.w_off + (uint32_t)num_w_stages * kWStageBytes;
     l.xchg_off = l.bias_off + 2 * kTileN * 4;
     l.bar_off = l.xchg_off + 2 * kTileM * 16;
-    // barriers: w_full[3] w_empty[3] s_full[3] s_empty[3] a_full[10] a_empty[10] acc_full[2] acc_empty[2] = 36,
+    // barriers: w_full[4] w_empty[4] (4 spare) a_full[10] a_empty[10] acc_full[2] acc_empty[2] = 36,
     // a_done[10] acc_done[2] (partner CTA only: local collection points relayed to the leader) = 48
     l.tmem_off = l.bar_off + 48 * 8;
     l.total = l.tmem_off + 16;
@@ -171,10 +176,12 @@ __device__ __forceinline__ float act_t(float x, float param) {
     return x;
 }
 
-// A producers: J k-blocks from the staged enc/dec slices.
+// A producers: J k-blocks straight from enc / dec in global memory (L1/L2 resident: every enc row of a tile is
+// read by tU threads, every dec row by tT).  The loads of k-block kb+1 are issued before block kb is processed,
+// so their latency hides behind the arithmetic and the a_empty wait.
 template <int MODE, int ACT, bool PAIR>
-__device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a, const uint8_t* slices,
-                                          uint64_t* s_full, uint64_t* s_empty, uint64_t* a_full, uint64_t* a_empty) {
+__device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a, const __nv_bfloat16* __restrict__ enc,
+                                          const __nv_bfloat16* __restrict__ dec, uint64_t* a_full, uint64_t* a_empty) {
     const Rounds<PAIR> rounds(p);
     // The partner CTA's producers arrive on a LOCAL barrier (a_full points at a_done there); a relay warp
     // forwards it to the leader.  A remote arrive has cluster-scope release semantics (MEMBAR.GPU), which in
@@ -184,9 +191,8 @@ __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a,
     const int c = ptid & 7;                                  // 16-byte chunk inside the 128-byte row
     const int rg = ptid >> 3;                                // rows rg, rg+32, rg+64, rg+96
     const int tT = 1 << p.tT_log2, tTm = tT - 1;
-    const int slot_bytes = (tT + (kTileM >> p.tT_log2)) * 128;
-    const int KB = p.KB, NSL = p.num_slice_slots;
-    uint32_t it = 0, slot = 0, sphase = 0;
+    const int KB = p.KB;
+    uint32_t it = 0;
     const bool slope_le1 = p.act_param >= 0.f && p.act_param <= 1.f;
     int ti[4], ui[4];
 #pragma unroll
@@ -199,7 +205,7 @@ __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a,
         int tile;
         TileCoord tc;
         if (!rounds.open(p, t0, tile, tc)) continue;
-        if (!tc.live) {  // dummy round: keep the pair's barrier protocol going, produce nothing
+        if (!tc.live || (p.dbg_skip & 2)) {  // dummy round: keep the pair's barrier protocol going, produce nothing
             for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(&a_empty[kb], (it & 1) ^ 1, 0x540 | kb);
                 __syncwarp();
@@ -209,22 +215,20 @@ __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a,
             continue;
         }
         bool ok[4];
+        const uint4* ep[4];
+        const uint4* dp[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ok[i] = tc.t0 + ti[i] < tc.Tb && tc.u0 + ui[i] < tc.Ub;
+        for (int i = 0; i < 4; ++i) {
+            ok[i] = tc.t0 + ti[i] < tc.Tb && tc.u0 + ui[i] < tc.Ub;
+            // rows outside the utterance are masked below; clamp them so that the loads stay inside the tensors
+            const int t = min(tc.t0 + ti[i], p.T - 1), u = min(tc.u0 + ui[i], p.U - 1);
+            ep[i] = reinterpret_cast<const uint4*>(enc + ((size_t)tc.b * p.T + t) * p.H) + c;
+            dp[i] = reinterpret_cast<const uint4*>(dec + ((size_t)tc.b * p.U + u) * p.H) + c;
+        }
+        uint4 ev[4], dv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ev[i] = __ldg(ep[i]); dv[i] = __ldg(dp[i]); }
         for (int kb = 0; kb < KB; ++kb) {
-            // slices of this k-block: rows [0, tT) = enc frames, rows [tT, tT + tU) = dec label positions
-            mbar_wait(&s_full[slot], sphase, 0x580 | slot);
-            const uint8_t* sl = slices + slot * slot_bytes;
-            uint4 ev[4], dv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                ev[i] = *reinterpret_cast<const uint4*>(sl + ti[i] * 128 + c * 16);
-                dv[i] = *reinterpret_cast<const uint4*>(sl + (tT + ui[i]) * 128 + c * 16);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[slot]);
-            if (++slot == (uint32_t)NSL) { slot = 0; sphase ^= 1; }
-
             uint4 o[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -243,6 +247,10 @@ __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a,
                     }
                     op[w] = ok[i] ? pack_bf16x2(a.x, a.y) : 0u;
                 }
+            }
+            if (kb + 1 < KB) {  // next k-block: 64 h further = 8 chunks of 16 bytes
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { ev[i] = __ldg(ep[i] + (kb + 1) * 8); dv[i] = __ldg(dp[i] + (kb + 1) * 8); }
             }
             mbar_wait(&a_empty[kb], (it & 1) ^ 1, 0x500 | kb);
             uint8_t* blk = smem_a + kb * kABlockBytes;
@@ -265,20 +273,16 @@ __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a,
 
 template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(kNumThreads, 1)
-joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_enc,
-                  const __grid_constant__ CUtensorMap tmap_dec, const JointParams p) {
+joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const SmemLayout L = smem_layout(p.KB, p.num_w_stages);
     uint8_t* smem_a = smem + L.a_off;
     uint8_t* smem_w = smem + L.w_off;
-    uint8_t* slices = smem + L.slice_off;
     float* bias_s = reinterpret_cast<float*>(smem + L.bias_off);
     float4* xchg = reinterpret_cast<float4*>(smem + L.xchg_off);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* w_full = bars;
-    uint64_t* w_empty = bars + 3;
-    uint64_t* s_full = bars + 6;
-    uint64_t* s_empty = bars + 9;
+    uint64_t* w_empty = bars + 4;
     uint64_t* a_full = bars + 12;
     uint64_t* a_empty = bars + 22;
     uint64_t* acc_full = bars + 32;
@@ -289,7 +293,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int KB = p.KB, NT = p.NT, NS = p.num_w_stages, NSL = p.num_slice_slots;
+    const int KB = p.KB, NT = p.NT, NS = p.num_w_stages;
     const Rounds<PAIR> rounds(p);
     const bool leader = rounds.rank == 0;
     constexpr uint32_t kCtas = PAIR ? 2 : 1;
@@ -298,14 +302,12 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B atoms need 1024-byte alignment
         // barriers the MMA lane waits on live in the leader CTA and collect arrivals from both CTAs
         for (int i = 0; i < NS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < NSL; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kNumProducerWarps); }
         // a_full / acc_empty (leader): its own 8 warps + one relayed arrival for the partner's 8 warps
         for (int i = 0; i < KB; ++i) { mbar_init(&a_full[i], kNumProducerWarps + (PAIR ? 1 : 0)); mbar_init(&a_empty[i], 1); mbar_init(&a_done[i], kNumProducerWarps); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kNumEpilogueWarps + (PAIR ? 1 : 0)); mbar_init(&acc_done[i], kNumEpilogueWarps); }
         fence_barrier_init();
     }
     if (warp_idx == kWarpTmaW && lane == 0) tma_prefetch_desc(&tmap_w);
-    if (warp_idx == kWarpTmaSlices && lane == 0) { tma_prefetch_desc(&tmap_enc); tma_prefetch_desc(&tmap_dec); }
     if (warp_idx == kWarpMma) {
         if (PAIR) tmem_alloc_2cta<512>(tmem_ptr);
         else tmem_alloc<512>(tmem_ptr);
@@ -320,17 +322,18 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         // ===================== W producer (TMA) =====================
         // PAIR: the leader fills BOTH halves of a stage (its own and, by multicast to CTA 1, its partner's),
         // so the refill latency is commit -> leader wake-up -> TMA, with no detour through the partner.
-        if (leader) {  // whole warp, converged; one lane is elected inside each issuing instruction
+        if (leader && !(p.dbg_skip & 4)) {  // whole warp, converged; one lane is elected inside each issuing instruction
             uint32_t stage = 0, phase = 0;
             for (int t0 = rounds.first; t0 < p.tile_end; t0 += rounds.step) {
                 int tile;
                 TileCoord tc;
                 if (!rounds.open(p, t0, tile, tc)) continue;
                 for (int nt = 0; nt < NT; ++nt) {
+                    const int vt = nt;
                     if (PAIR) {
-                        // CTA r holds rows [nt*256 + r*N/2, +128) of the vocabulary tile
-                        const int n_cur = nt == NT - 1 ? p.n_last : kTileN;
-                        const int row0 = nt * kTileN, row1 = row0 + (n_cur >> 1);
+                        // CTA r holds rows [vt*256 + r*N/2, +128) of the vocabulary tile
+                        const int n_cur = vt == NT - 1 ? p.n_last : kTileN;
+                        const int row0 = vt * kTileN, row1 = row0 + (n_cur >> 1);
                         for (int kb = 0; kb < KB; ++kb) {
                             mbar_wait(&w_empty[stage], phase ^ 1, 0x100 | stage);
                             __syncwarp();
@@ -345,7 +348,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                             mbar_wait(&w_empty[stage], phase ^ 1, 0x100 | stage);
                             __syncwarp();
                             mbar_arrive_expect_tx_e(&w_full[stage], kWStageBytes);
-                            tma_load_2d_e(smem_w + stage * kWStageBytes, &tmap_w, &w_full[stage], ks * kWStageK, nt * kTileN);
+                            tma_load_2d_e(smem_w + stage * kWStageBytes, &tmap_w, &w_full[stage], ks * kWStageK, vt * kTileN);
                             if (++stage == (uint32_t)NS) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -394,7 +397,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                         }
                         if (PAIR) {
                             if (p.prof) tm = clock64();
-                            mbar_wait(&w_full[stage], phase, 0x400 | stage);
+                            if (!(p.dbg_skip & 4)) mbar_wait(&w_full[stage], phase, 0x400 | stage);
                             if (p.prof) t_w += clock64() - tm;
                             tcgen05_fence_after();
                             const uint32_t w_lo = w_lo0 + stage * (kWStageBytes >> 4);
@@ -403,7 +406,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                             umma_bf16_2cta_x4_e(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)w_hi << 32) | w_lo, idesc, kb != 0);
                             if (p.prof) { l_sum += clock64() - tm; ++l_cnt; }
                             if (p.prof) tm = clock64();
-                            umma_commit_2cta_e(&w_empty[stage], 1);  // only the leader refills
+                            if (!(p.dbg_skip & 4)) umma_commit_2cta_e(&w_empty[stage], 1);  // only the leader refills
                             if (++stage == (uint32_t)NS) { stage = 0; phase ^= 1; }
                             if (last_nt) umma_commit_2cta_e(&a_empty[kb], 3);
                             if (p.prof) t_commit[0] += clock64() - tm;
@@ -465,35 +468,14 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 ++it;
             }
         }
-    } else if (warp_idx == kWarpTmaSlices) {
-        // ===================== enc / dec slice producer (TMA) =====================
-        {  // whole warp, converged
-            const int tT = 1 << p.tT_log2, tU = kTileM >> p.tT_log2;
-            const int slot_bytes = (tT + tU) * 128;
-            uint32_t slot = 0, phase = 0;
-            for (int t0 = rounds.first; t0 < p.tile_end; t0 += rounds.step) {
-                int tile;
-                TileCoord tc;
-                if (!rounds.open(p, t0, tile, tc) || !tc.live) continue;
-                for (int kb = 0; kb < KB; ++kb) {
-                    mbar_wait(&s_empty[slot], phase ^ 1, 0x180 | slot);
-                    __syncwarp();
-                    uint8_t* sl = slices + slot * slot_bytes;
-                    mbar_arrive_expect_tx_e(&s_full[slot], slot_bytes);
-                    tma_load_2d_e(sl, &tmap_enc, &s_full[slot], kb * kABlockK, tc.b * p.T + tc.t0);
-                    tma_load_2d_e(sl + tT * 128, &tmap_dec, &s_full[slot], kb * kABlockK, tc.b * p.U + tc.u0);
-                    if (++slot == (uint32_t)NSL) { slot = 0; phase ^= 1; }
-                }
-            }
-        }
     } else if (warp_idx >= kFirstProducerWarp && warp_idx < kFirstProducerWarp + kNumProducerWarps) {
         // ===================== A producers: J = bf16(act(enc + dec)) =====================
         uint64_t* a_arrive = (PAIR && !leader) ? a_done : a_full;
         switch (p.act_kind) {
-            case ACT_LEAKY_RELU: produce_a<MODE, ACT_LEAKY_RELU, PAIR>(p, smem_a, slices, s_full, s_empty, a_arrive, a_empty); break;
-            case ACT_RELU: produce_a<MODE, ACT_RELU, PAIR>(p, smem_a, slices, s_full, s_empty, a_arrive, a_empty); break;
-            case ACT_TANH: produce_a<MODE, ACT_TANH, PAIR>(p, smem_a, slices, s_full, s_empty, a_arrive, a_empty); break;
-            default: produce_a<MODE, ACT_IDENTITY, PAIR>(p, smem_a, slices, s_full, s_empty, a_arrive, a_empty); break;
+            case ACT_LEAKY_RELU: produce_a<MODE, ACT_LEAKY_RELU, PAIR>(p, smem_a, p.enc, p.dec, a_arrive, a_empty); break;
+            case ACT_RELU: produce_a<MODE, ACT_RELU, PAIR>(p, smem_a, p.enc, p.dec, a_arrive, a_empty); break;
+            case ACT_TANH: produce_a<MODE, ACT_TANH, PAIR>(p, smem_a, p.enc, p.dec, a_arrive, a_empty); break;
+            default: produce_a<MODE, ACT_IDENTITY, PAIR>(p, smem_a, p.enc, p.dec, a_arrive, a_empty); break;
         }
     } else if (warp_idx < kFirstEpilogueWarp + kNumEpilogueWarps) {
         // ===================== epilogue =====================
@@ -515,7 +497,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             int tile;
             TileCoord tc;
             if (!rounds.open(p, t0, tile, tc)) continue;
-            if (!tc.live) {  // dummy round: release the accumulators the pair's MMA stream wrote for us
+            if (!tc.live || (p.dbg_skip & 1)) {  // dummy round: release the accumulators the pair's MMA stream wrote for us
                 for (int nt = 0; nt < NT; ++nt, ++acc_it) {
                     const uint32_t buf = acc_it & 1;
                     mbar_wait(&acc_full[buf], (acc_it >> 1) & 1, 0x640 | buf);
@@ -565,9 +547,10 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 // stage bias * log2(e) for this vocabulary tile (one buffer per group).  The values were
                 // loaded into registers while the group's previous tile was being processed, so the L2
                 // latency of the load is off the critical path.
+                const int vt = nt;
                 {
-                    if (nb_nt != nt) {  // first tile of the kernel
-                        const int v0 = nt * kTileN + grp * kGrpCols + gtid;
+                    if (nb_nt != vt) {  // first tile of the kernel
+                        const int v0 = vt * kTileN + grp * kGrpCols + gtid;
                         nb0 = v0 < p.V ? __ldg(p.bias + v0) : 0.f;
                     }
                     asm volatile("bar.sync %0, 128;" ::"r"(4 + grp) : "memory");  // previous tile's reads are done
@@ -579,12 +562,12 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 }
                 mbar_wait(&acc_full[buf], acc_phase, 0x600 | buf);
                 tcgen05_fence_after();
-                const int n_all = nt == NT - 1 ? p.n_last : kTileN;
+                const int n_all = vt == NT - 1 ? p.n_last : kTileN;
                 const int c_begin = grp * kGrpCols, n_cols = min(n_all, c_begin + kGrpCols);  // this group's columns [c_begin, n_cols)
                 // TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c is processed
                 uint32_t raw0[16], raw1[16];
                 auto process = [&](const uint32_t (&raw)[16], const int cc) {
-                    const int col0 = nt * kTileN + cc;
+                    const int col0 = vt * kTileN + cc;
                     // y = logit * log2(e) = acc * log2(e) + bias * log2(e), two columns per instruction
                     float2 y2[8];
                     const float4* b4 = reinterpret_cast<const float4*>(bias_g + (cc - c_begin));
@@ -705,9 +688,9 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 if (MODE == MODE_GRAD && n_all < kTileN) {
                     // zero-fill the 16-column chunks of the last tile the MMA did not produce, so the
                     // backward GEMMs read finite zeros for the padded vocabulary columns
-                    const int cols_pad = min(((p.V + 63) / 64) * 64 - nt * kTileN, c_begin + kGrpCols);  // columns the images cover
+                    const int cols_pad = min(((p.V + 63) / 64) * 64 - vt * kTileN, c_begin + kGrpCols);  // columns the images cover
                     for (int cc = max(n_all, c_begin); cc < cols_pad; cc += 16) {
-                        const int col0 = nt * kTileN + cc;
+                        const int col0 = vt * kTileN + cc;
                         uint8_t* img = reinterpret_cast<uint8_t*>(p.dY_img) +
                                        ((size_t)(tile - p.tile_begin) * (NT * 4) + (col0 >> 6)) * kABlockBytes;
                         const int chunk0 = (col0 & 63) >> 3;
