@@ -190,6 +190,33 @@ def run_reference(args, rank):
     }))
 
 
+def kernel_lines(kernel_ms, cells, H, V, B, T, U, peak_tf, peak_hbm):
+    """Per-kernel device time of one step (CUDA events inside the library, 5 extra steps after the timed region)
+    with the bound that applies: GEMM kernels against the measured bf16 peak (2*M*H*V FLOPs each), the lattice
+    DP and the fold kernels against the measured HBM copy bandwidth (algorithmic bytes)."""
+    gemm = 2.0 * cells * H * V
+    tiles = B * ((T + 15) // 16) * ((U + 7) // 8)
+    algo = {
+        "joint_gemm_kernel<FWD>": ("tensor", gemm), "joint_gemm_kernel<GRAD>": ("tensor", gemm),
+        "dj_gemm_kernel": ("tensor", gemm), "dw_gemm_kernel": ("tensor", gemm),
+        "alpha_beta_kernel": ("hbm", 24.0 * cells),
+        "reduce_dpre_kernel": ("hbm", 4.0 * (tiles * 24 * H + B * T * H + 2 * B * U * H)),
+        "reduce_dw_kernel": ("hbm", 4.0 * V * H * 10),
+    }
+    lines = []
+    for name, ms in kernel_ms.items():
+        bound, work = algo.get(name, (None, None))
+        line = {"kernel": name, "ms": round(ms, 4)}
+        if bound == "tensor":
+            a = work / (ms / 1e3) / 1e12
+            line.update(bound="tensor", achieved=round(a, 1), unit="TFLOP/s", frac=round(a / peak_tf, 3))
+        elif bound == "hbm":
+            a = work / (ms / 1e3) / 1e9
+            line.update(bound="hbm", achieved=round(a, 1), unit="GB/s", frac=round(a / peak_hbm, 3))
+        lines.append(line)
+    return lines
+
+
 def workload_name():
     return ("conformer-t_scratch joint+RNN-T loss fwd+bwd, synthetic B=16 T=400 U=100 V=1000 H=640 per GPU, "
             "bf16 joint / fp32 lattice (BASELINE configs[1]; configs[2] at N>1)")
@@ -339,6 +366,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * cells / (t.item() / 1e3)
 
+    # ---- per-kernel pass (after the timed regions): the library brackets each of its launches with CUDA events ----
+    kernel_ms = {}
+    if rank == 0:
+        _lib.kernel_timing(True)
+        n_prof = 5
+        for _ in range(n_prof):
+            flush.zero_()
+            step(False)
+        torch.cuda.synchronize()
+        kernel_ms = {k: v[0] / n_prof for k, v in _lib.kernel_timings().items()}
+        _lib.kernel_timing(False)
+
     out = None
     if rank == 0:
         peak_tf, peak_hbm, peak_src = measured_peaks()
@@ -365,6 +404,7 @@ def main():
                          "algorithmic_flops_per_launch": flops,
                          "step_frac_of_6MHV_roofline": (6.0 * cells * H * V / (ms_per_step / 1e3) / 1e12) / peak_tf},
             "clocks": clocks,
+            "kernels": kernel_lines(kernel_ms, cells, H, V, B, T, U, peak_tf, peak_hbm),
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -120,6 +120,14 @@ int tsasr_joint_debug_logits(const void* enc, const void* dec, const void* W, co
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 long long tsasr_launch_count(void);
 
+/* Measurement aid (bench.py's per-kernel roofline lines): while enabled, every kernel launch of this
+ * library is bracketed by two CUDA events on the launching stream (no host synchronisation).
+ * tsasr_kernel_timings() waits for the recorded events, sums them per kernel name and clears the record:
+ * names is max_n x 32 chars, ms / counts are max_n entries; returns the number of distinct kernels.
+ * The reference has no counterpart (it times nothing on the device). */
+int tsasr_kernel_timing_enable(int on);
+int tsasr_kernel_timings(char* names, float* ms, int* counts, int max_n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,8 @@ SIGNATURES = {
     "tsasr_joint_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "tsasr_joint_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _ll]),
     "tsasr_joint_bwd": (_i, [_vp] * 7 + [_i] * 7 + [_f] + [_vp] * 7 + [_sz, _ll] + [_vp] * 5),
+    "tsasr_kernel_timing_enable": (_i, [_i]),
+    "tsasr_kernel_timings": (_i, [ctypes.c_char_p, _vp, _vp, _i]),
     "tsasr_joint_debug_logits": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
 }
 
@@ -67,3 +69,20 @@ def check(rc):
 
 def launch_count():
     return int(load().tsasr_launch_count())
+
+
+def kernel_timing(on):
+    """Bracket every kernel launch of the library with CUDA events (measurement aid, no host sync)."""
+    load().tsasr_kernel_timing_enable(1 if on else 0)
+
+
+def kernel_timings(max_n=32):
+    """-> {kernel name: (total ms, launches)} since the last call; waits for the recorded events."""
+    names = ctypes.create_string_buffer(32 * max_n)
+    ms = (ctypes.c_float * max_n)()
+    counts = (ctypes.c_int * max_n)()
+    n = load().tsasr_kernel_timings(names, ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(counts, ctypes.c_void_p), max_n)
+    out = {}
+    for i in range(n):
+        out[names.raw[32 * i: 32 * i + 32].split(b"\0")[0].decode()] = (float(ms[i]), int(counts[i]))
+    return out

@@ -21,39 +21,34 @@ struct BwdPlan {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// development: TSASR_DEBUG_TIMING=1 brackets every backward launch with CUDA events on the launching
-// stream and prints the per-kernel milliseconds to stderr (synchronises; never on in production).
+// development: TSASR_DEBUG_TIMING=1 prints the per-kernel milliseconds of every backward call to stderr
+// (synchronises; never on in production).  Uses the same event brackets as tsasr_kernel_timing_enable().
 struct KernelTimer {
-    static constexpr int kMax = 64;
-    bool on;
-    cudaStream_t st;
-    int n = 0;
-    const char* names[kMax];
-    cudaEvent_t ev[kMax + 1];
-    explicit KernelTimer(cudaStream_t s) : st(s) {
+    bool on, was_on;
+    int first;
+    KernelTimer() {
         static const bool enabled = getenv("TSASR_DEBUG_TIMING") != nullptr;
         on = enabled;
-        if (on) { cudaEventCreate(&ev[0]); cudaEventRecord(ev[0], st); }
-    }
-    void mark(const char* name) {
-        if (!on || n >= kMax) return;
-        names[n] = name;
-        cudaEventCreate(&ev[n + 1]);
-        cudaEventRecord(ev[n + 1], st);
-        ++n;
+        was_on = g_timing_on;
+        first = g_n_timed;
+        if (on) g_timing_on = true;
     }
     ~KernelTimer() {
         if (!on) return;
-        cudaStreamSynchronize(st);
         float total = 0.f;
-        for (int i = 0; i < n; ++i) {
+        for (int i = first; i < g_n_timed; ++i) {
             float ms = 0.f;
-            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            cudaEventSynchronize(g_timed[i].e1);
+            cudaEventElapsedTime(&ms, g_timed[i].e0, g_timed[i].e1);
             total += ms;
-            fprintf(stderr, "[tsasr timing] %-28s %8.3f ms\n", names[i], ms);
+            fprintf(stderr, "[tsasr timing] %-28s %8.3f ms\n", g_timed[i].name, ms);
         }
-        fprintf(stderr, "[tsasr timing] %-28s %8.3f ms\n", "backward total", total);
-        for (int i = 0; i <= n; ++i) cudaEventDestroy(ev[i]);
+        fprintf(stderr, "[tsasr timing] %-28s %8.3f ms\n", "backward kernels total", total);
+        if (!was_on) {  // nobody will collect these events
+            for (int i = first; i < g_n_timed; ++i) { cudaEventDestroy(g_timed[i].e0); cudaEventDestroy(g_timed[i].e1); }
+            g_n_timed = first;
+            g_timing_on = false;
+        }
     }
 };
 
@@ -239,14 +234,15 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
     const int total_tiles = B * jp.nTt * jp.nTu;
     const int tU = 128 >> jp.tT_log2;
     int chunk_idx = 0;
-    KernelTimer timer(st);
-    timer.mark("memsets");
+    KernelTimer timer;
     for (int t0 = 0; t0 < total_tiles; t0 += pl.chunk_tiles, ++chunk_idx) {
         const int t1 = t0 + pl.chunk_tiles < total_tiles ? t0 + pl.chunk_tiles : total_tiles;
         jp.tile_begin = bp.tile_begin = t0;
         jp.tile_end = bp.tile_end = t1;
-        if (int rc = launch_joint<MODE_GRAD>(maps, jp, sms, st)) return rc;
-        timer.mark("joint_gemm<GRAD>");
+        {
+            ScopedTiming tm("joint_gemm_kernel<GRAD>", st);
+            if (int rc = launch_joint<MODE_GRAD>(maps, jp, sms, st)) return rc;
+        }
 
         {
             const int dj_cs = 2;
@@ -274,7 +270,10 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
                 cudaMemset(d_prof, 0, sizeof(long long) * 4 * n_clusters * dj_cs);
                 bpp.prof = d_prof;
             }
-            e = cudaLaunchKernelEx(&cfg, dj_kern, tmap_dj, tmap_dy, bpp);
+            {
+                ScopedTiming tm("dj_gemm_kernel", st);
+                e = cudaLaunchKernelEx(&cfg, dj_kern, tmap_dj, tmap_dy, bpp);
+            }
             if (prof_on) {
                 cudaStreamSynchronize(st);
                 const int n = n_clusters * dj_cs;
@@ -292,7 +291,6 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
             ++g_launches;
             if (e != cudaSuccess) return cuda_fail(e, "dj_gemm_kernel launch");
             if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "dj_gemm_kernel launch");
-            timer.mark("dj_gemm");
         }
 
         {
@@ -300,10 +298,10 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
             const int g0 = t0 / jp.nTu, g1 = t1 / jp.nTu;
             const int b0 = g0 / jp.nTt, b1 = (g1 - 1) / jp.nTt + 1;
             const int rows = (g1 - g0) * tT + (b1 - b0) * U;
+            ScopedTiming tm("reduce_dpre_kernel", st);
             reduce_dpre_kernel<<<rows, 160, 0, st>>>(bp, d_enc, d_dec);
             ++g_launches;
             if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "reduce_dpre_kernel launch");
-            timer.mark("reduce_dpre");
         }
 
         bp.accumulate = chunk_idx > 0;
@@ -330,7 +328,10 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
                 cudaMemset(d_prof, 0, sizeof(long long) * 4 * n);
                 bpp.prof = d_prof;
             }
-            e = cudaLaunchKernelEx(&cfg, dw_gemm_kernel, tmap_dy_half, tmap_j_half, bpp);
+            {
+                ScopedTiming tm("dw_gemm_kernel", st);
+                e = cudaLaunchKernelEx(&cfg, dw_gemm_kernel, tmap_dy_half, tmap_j_half, bpp);
+            }
             if (prof_on) {
                 cudaStreamSynchronize(st);
                 long long* h = new long long[4 * n];
@@ -350,13 +351,14 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
         }
         ++g_launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "dw_gemm_kernel launch");
-        timer.mark("dw_gemm");
     }
     (void)tU;
-    reduce_dw_kernel<<<sms * 2, 256, 0, st>>>(bp, dW, db);
+    {
+        ScopedTiming tm("reduce_dw_kernel", st);
+        reduce_dw_kernel<<<sms * 2, 256, 0, st>>>(bp, dW, db);
+    }
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "reduce_dw_kernel launch");
-    timer.mark("reduce_dw");
     return TSASR_OK;
 }
 

@@ -47,6 +47,29 @@ static int cuda_fail(cudaError_t e, const char* what) {
     return fail(TSASR_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 
+// ---- optional per-kernel timing (measurement aid, see tsasr_kernel_timing_enable) ----
+// Every launch site is bracketed by two CUDA events on the launching stream; nothing synchronises until
+// tsasr_kernel_timings() is called.  Not thread-safe by design (bench.py / tools are single-threaded).
+struct TimedLaunch { const char* name; cudaEvent_t e0, e1; };
+static bool g_timing_on = false;
+static TimedLaunch g_timed[4096];
+static int g_n_timed = 0;
+struct ScopedTiming {
+    int idx = -1;
+    cudaStream_t st;
+    ScopedTiming(const char* name, cudaStream_t s) : st(s) {
+        if (!g_timing_on || g_n_timed >= 4096) return;
+        idx = g_n_timed++;
+        g_timed[idx].name = name;
+        cudaEventCreate(&g_timed[idx].e0);
+        cudaEventCreate(&g_timed[idx].e1);
+        cudaEventRecord(g_timed[idx].e0, st);
+    }
+    ~ScopedTiming() {
+        if (idx >= 0) cudaEventRecord(g_timed[idx].e1, st);
+    }
+};
+
 #define REQUIRE(cond, ...) \
     do {                   \
         if (!(cond)) return fail(TSASR_E_INVALID, __VA_ARGS__); \
@@ -255,6 +278,37 @@ int tsasr_abi_version(void) { return TSASR_ABI_VERSION; }
 const char* tsasr_last_error(void) { return g_err; }
 long long tsasr_launch_count(void) { return g_launches.load(); }
 
+int tsasr_kernel_timing_enable(int on) {
+    g_timing_on = on != 0;
+    return TSASR_OK;
+}
+
+int tsasr_kernel_timings(char* names, float* ms, int* counts, int max_n) {
+    int n = 0;
+    for (int i = 0; i < g_n_timed; ++i) {
+        float t = 0.f;
+        cudaEventSynchronize(g_timed[i].e1);
+        cudaEventElapsedTime(&t, g_timed[i].e0, g_timed[i].e1);
+        cudaEventDestroy(g_timed[i].e0);
+        cudaEventDestroy(g_timed[i].e1);
+        int k = 0;
+        for (; k < n; ++k)
+            if (strncmp(names + 32 * k, g_timed[i].name, 31) == 0) break;
+        if (k == n) {
+            if (n >= max_n) continue;
+            strncpy(names + 32 * n, g_timed[i].name, 31);
+            names[32 * n + 31] = 0;
+            ms[n] = 0.f;
+            counts[n] = 0;
+            ++n;
+        }
+        ms[k] += t;
+        counts[k] += 1;
+    }
+    g_n_timed = 0;
+    return n;
+}
+
 size_t tsasr_lattice_elems(int B, int T, int U) { return (size_t)B * (size_t)(T + U - 1) * (size_t)U; }
 
 int tsasr_logits_to_lattice(const void* logits, int logits_dtype, const int32_t* targets, const int32_t* logit_lengths,
@@ -264,6 +318,7 @@ int tsasr_logits_to_lattice(const void* logits, int logits_dtype, const int32_t*
     REQUIRE(logits && logit_lengths && target_lengths && lat2 && den, "null pointer argument");
     REQUIRE(U == 1 || targets, "targets must not be null when U > 1");
     REQUIRE(logits_dtype >= 0 && logits_dtype <= 2, "unknown logits dtype %d", logits_dtype);
+    ScopedTiming tm("logits_to_lattice_kernel", static_cast<cudaStream_t>(stream));
     cudaError_t e = launch_logits_to_lattice(logits, logits_dtype, targets, logit_lengths, target_lengths, B, T, U, V,
                                              blank, normalized, reinterpret_cast<float2*>(lat2), den,
                                              static_cast<cudaStream_t>(stream));
@@ -277,6 +332,7 @@ int tsasr_lattice_alpha_beta(const float* lat2, const int32_t* logit_lengths, co
     if (int rc = check_dims(B, T, U, 1, 0)) return rc;
     REQUIRE(lat2 && logit_lengths && target_lengths && alpha && beta && cost && ll_alpha && ll_beta, "null pointer argument");
     if (U > 1024) return fail(TSASR_E_UNSUPPORTED, "lattice width U=%d > 1024 is not supported (the reference's Numba kernels share this limit)", U);
+    ScopedTiming tm("alpha_beta_kernel", static_cast<cudaStream_t>(stream));
     cudaError_t e = launch_alpha_beta(reinterpret_cast<const float2*>(lat2), logit_lengths, target_lengths, B, T, U,
                                       alpha, beta, ll_alpha, ll_beta, cost, static_cast<cudaStream_t>(stream));
     g_launches += 2;
@@ -291,6 +347,7 @@ int tsasr_logits_grad(const void* logits, int logits_dtype, const int32_t* targe
     REQUIRE(logits && logit_lengths && target_lengths && lat2 && den && alpha && beta && cost && dlogits, "null pointer argument");
     REQUIRE(U == 1 || targets, "targets must not be null when U > 1");
     REQUIRE(logits_dtype >= 0 && logits_dtype <= 2, "unknown logits dtype %d", logits_dtype);
+    ScopedTiming tm("logits_grad_kernel", static_cast<cudaStream_t>(stream));
     cudaError_t e = launch_logits_grad(logits, logits_dtype, targets, logit_lengths, target_lengths, B, T, U, V, blank,
                                        reinterpret_cast<const float2*>(lat2), den, alpha, beta, cost, dcost, clamp,
                                        dlogits, static_cast<cudaStream_t>(stream));
@@ -304,6 +361,7 @@ int tsasr_logprobs_grad(const int32_t* targets, const int32_t* logit_lengths, co
     if (int rc = check_dims(B, T, U, V, blank)) return rc;
     REQUIRE(logit_lengths && target_lengths && lat2 && alpha && beta && cost && grads, "null pointer argument");
     REQUIRE(U == 1 || targets, "targets must not be null when U > 1");
+    ScopedTiming tm("logprobs_grad_kernel", static_cast<cudaStream_t>(stream));
     cudaError_t e = launch_logprobs_grad(targets, logit_lengths, target_lengths, B, T, U, V, blank,
                                          reinterpret_cast<const float2*>(lat2), alpha, beta, cost, dcost, grads,
                                          static_cast<cudaStream_t>(stream));
@@ -327,6 +385,7 @@ int tsasr_joint_fwd(const void* enc, const void* dec, const void* W, const float
     p.logz = logz;
     JointMaps maps;
     if (int rc = make_joint_maps(&maps, p, enc, dec, W)) return rc;
+    ScopedTiming tm("joint_gemm_kernel<FWD>", static_cast<cudaStream_t>(stream));
     return launch_joint<MODE_FWD>(maps, p, sms, static_cast<cudaStream_t>(stream));
 }
 
