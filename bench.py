@@ -250,7 +250,10 @@ def main():
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        import datetime
+
+        # a short collective timeout: a rank-divergence bug must fail in seconds, not hold the box for 10 minutes
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=120))
     W_steps = max(3, args.warmup)
     K = max(1, args.steps)
 
@@ -367,16 +370,15 @@ def main():
     e2e_value = world * cells / (t.item() / 1e3)
 
     # ---- per-kernel pass (after the timed regions): the library brackets each of its launches with CUDA events ----
-    kernel_ms = {}
-    if rank == 0:
-        _lib.kernel_timing(True)
-        n_prof = 5
-        for _ in range(n_prof):
-            flush.zero_()
-            step(False)
-        torch.cuda.synchronize()
-        kernel_ms = {k: v[0] / n_prof for k, v in _lib.kernel_timings().items()}
-        _lib.kernel_timing(False)
+    # (every rank runs the steps -- they contain the all-reduce -- rank 0 reports its own kernels)
+    _lib.kernel_timing(True)
+    n_prof = 5
+    for _ in range(n_prof):
+        flush.zero_()
+        step(False)
+    torch.cuda.synchronize()
+    kernel_ms = {k: v[0] / n_prof for k, v in _lib.kernel_timings().items()}
+    _lib.kernel_timing(False)
 
     out = None
     if rank == 0:
