@@ -214,3 +214,30 @@ def test_drop_in_modules_vs_golden(golden, name):
     np.testing.assert_allclose(loss.item(), g["loss"], rtol=LOSS_RTOL)
     for got, key in ((enc.grad, "d_enc"), (dec.grad, "d_dec"), (head.weight.grad, "dW"), (head.bias.grad, "db")):
         assert _rel_err(got.cpu(), torch.tensor(g[key])) < GRAD_REL, key
+
+
+def test_fused_length_precondition_errors_are_raised_after_safe_launch():
+    """The fused path validates lengths on a side stream AFTER queueing its kernels (they clamp every length to the
+    padded lattice): the same RuntimeErrors as torchaudio must come out and the device must stay healthy."""
+    B, T, U, H, V = 2, 24, 9, 64, 40
+    enc, dec, W, b, targets, ll, tl = _inputs(B, T, U, H, V, seed=77, ragged=False)
+    d = _dev()
+    args = [x.to(d) for x in (enc.float(), dec.float(), W.float(), b, targets)]
+
+    def call(ll_, tl_):
+        return tsasr_b200.fused_joint_rnnt_loss(*args, ll_.to(d), tl_.to(d), blank=0, reduction="none")
+
+    with pytest.raises(RuntimeError, match="input length mismatch"):
+        call(torch.tensor([T + 500, T], dtype=torch.int32), tl)
+    with pytest.raises(RuntimeError, match="input length mismatch"):
+        call(torch.tensor([T - 1, T - 2], dtype=torch.int32), tl)
+    with pytest.raises(RuntimeError, match="output length mismatch"):
+        call(ll, torch.tensor([U + 300, U - 1], dtype=torch.int32))
+    with pytest.raises(RuntimeError, match="logit_lengths must be >= 1"):
+        call(torch.tensor([T, 0], dtype=torch.int32), tl)
+    with pytest.raises(RuntimeError, match="logit_lengths must be >= 1"):
+        call(ll, torch.tensor([U - 1, -3], dtype=torch.int32))
+    torch.cuda.synchronize()
+    costs = call(ll, tl)  # a valid call afterwards: finite, matches the reference
+    ref = reference_joint_loss_fwd_bwd(enc, dec, W, b, targets, ll, tl, 0, "leaky_relu", 0.01, round_bf16=True)
+    np.testing.assert_allclose(costs.cpu().numpy(), ref["costs"].numpy(), rtol=LOSS_RTOL)

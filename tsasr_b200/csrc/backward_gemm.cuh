@@ -62,7 +62,8 @@ __device__ __forceinline__ bool tile_live(const BwdParams& p, int tile) {
     const int b = tile / per_b;
     const int rem = tile - b * per_b;
     const int tt = rem / p.nTu, tu = rem - tt * p.nTu;
-    return (tt << p.tT_log2) < p.logit_lengths[b] && tu * (kTileM >> p.tT_log2) < p.target_lengths[b] + 1;
+    const int Tb = min(max(p.logit_lengths[b], 1), p.T), Ub = min(max(p.target_lengths[b], 0), p.U - 1) + 1;
+    return (tt << p.tT_log2) < Tb && tu * (kTileM >> p.tT_log2) < Ub;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -332,8 +333,8 @@ reduce_dpre_kernel(const BwdParams p, float* __restrict__ d_enc, float* __restri
         const int g = g_begin + gl;
         const int b = g / p.nTt, tt = g - b * p.nTt;
         const int t = tt * tT + ti;
-        if (t >= p.logit_lengths[b]) return;  // rows beyond T_b stay zero (memset)
-        const int n_tu = (p.target_lengths[b] + 1 + tU - 1) / tU;  // live label tiles
+        if (t >= min(max(p.logit_lengths[b], 1), p.T)) return;  // rows beyond T_b stay zero (memset)
+        const int n_tu = (min(max(p.target_lengths[b], 0), p.U - 1) + 1 + tU - 1) / tU;  // live label tiles
         for (int h4 = threadIdx.x; h4 < H4; h4 += blockDim.x) {
             const float4* base = part + ((size_t)gl * p.nTu) * tile_stride4 + (size_t)ti * H4 + h4;
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -348,8 +349,8 @@ reduce_dpre_kernel(const BwdParams p, float* __restrict__ d_enc, float* __restri
         const int row = blockIdx.x - n_enc_rows;
         const int b_begin = g_begin / p.nTt;
         const int b = b_begin + row / p.U, u = row % p.U;
-        if (u >= p.target_lengths[b] + 1) return;
-        const int Tb = p.logit_lengths[b];
+        if (u >= min(max(p.target_lengths[b], 0), p.U - 1) + 1) return;
+        const int Tb = min(max(p.logit_lengths[b], 1), p.T);
         const int tu = u / tU, ui = u - tu * tU;
         const int gb0 = max(g_begin, b * p.nTt), gb1 = min(min(g_end, (b + 1) * p.nTt), b * p.nTt + (Tb + tT - 1) / tT);
         for (int h4 = threadIdx.x; h4 < H4; h4 += blockDim.x) {

@@ -122,8 +122,8 @@ __device__ __forceinline__ TileCoord tile_coord(const JointParams& p, int tile) 
     const int tT = 1 << p.tT_log2, tU = kTileM >> p.tT_log2;
     c.t0 = tt * tT;
     c.u0 = tu * tU;
-    c.Tb = p.logit_lengths[c.b];
-    c.Ub = p.target_lengths[c.b] + 1;
+    c.Tb = min(max(p.logit_lengths[c.b], 1), p.T);          // clamped: validated on the host after launching
+    c.Ub = min(max(p.target_lengths[c.b], 0), p.U - 1) + 1;
     c.live = c.t0 < c.Tb && c.u0 < c.Ub;
     return c;
 }

@@ -251,7 +251,9 @@ alpha_beta_kernel(const float2* __restrict__ lat2, const int* __restrict__ logit
     __shared__ float xchg[64];
     extern __shared__ __align__(16) float2 dp_ring[];  // [kDpPrefetch][blockDim.x]
     const int b = blockIdx.x;
-    const int Tb = logit_lengths[b], Ub = target_lengths[b] + 1;
+    // lengths are clamped to the padded lattice: the fused path validates them on the host only after
+    // launching (tsasr_b200/functional.py), so an invalid length must never index outside the slab
+    const int Tb = min(max(logit_lengths[b], 1), Tmax), Ub = min(max(target_lengths[b], 0), U - 1) + 1;
     const size_t base = (size_t)b * (size_t)(Tmax + U - 1) * (size_t)U;
     // Each utterance's own rectangle starts at diagonal 0 of its slab: cell (t,u) -> row t+u.
     if (blockIdx.y == 0) dp_pass<false>(lat2 + base, alpha + base, Tb, Ub, U, ll_alpha + b, xchg, dp_ring);

@@ -38,6 +38,45 @@ def _validate_lengths(logit_lengths, target_lengths, T, U, n_targets):
         raise RuntimeError("logit_lengths must be >= 1 and target_lengths >= 0")
 
 
+class _DeferredLengthCheck:
+    """The same host-side checks, but read back on a side stream: the statistics are computed by tiny kernels
+    on the caller's stream BEFORE the fused kernels are queued and copied to pinned memory on a second stream,
+    so the host only waits for those tiny kernels while the GPU already works on the joint GEMM.  The fused
+    kernels clamp every length to the padded lattice, so an invalid input cannot index out of bounds before
+    ``finish`` raises (same exception types and messages as ``_validate_lengths``)."""
+
+    _side, _pinned = {}, {}
+
+    def __init__(self, logit_lengths, target_lengths):
+        dev = logit_lengths.device
+        stats = torch.stack([logit_lengths.max(), target_lengths.max(), logit_lengths.min(), target_lengths.min()])
+        side = self._side.get(dev)
+        if side is None:
+            side = self._side[dev] = torch.cuda.Stream(dev)
+            self._pinned[dev] = torch.empty((4,), dtype=stats.dtype).pin_memory()
+        self.host = self._pinned[dev]
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            self.host.copy_(stats, non_blocking=True)
+            self.done = torch.cuda.Event()
+            self.done.record(side)
+        stats.record_stream(side)
+
+    def finish(self, T, U, n_targets):
+        self.done.synchronize()
+        max_t, max_l, min_t, min_l = (int(v) for v in self.host.tolist())
+        if max_t != T:
+            raise RuntimeError("input length mismatch")
+        if max_l + 1 != U:
+            raise RuntimeError("output length mismatch")
+        if n_targets != max_l:
+            raise RuntimeError("target length mismatch")
+        if min_t < 1 or min_l < 0:
+            raise RuntimeError("logit_lengths must be >= 1 and target_lengths >= 0")
+
+
 class RnntLossFromLogits(torch.autograd.Function):
     """costs[b] = -log P(y_b | x_b) from materialised logits; backward emits dense dlogits.
 
@@ -188,8 +227,9 @@ def fused_joint_rnnt_loss(enc_out, dec_out, weight, bias, targets, logit_lengths
     targets = targets.to(torch.int32).contiguous()
     logit_lengths = logit_lengths.to(torch.int32).contiguous()
     target_lengths = target_lengths.to(torch.int32).contiguous()
-    if check_lengths:
-        _validate_lengths(logit_lengths, target_lengths, T, U, targets.shape[1])
+    check = _DeferredLengthCheck(logit_lengths, target_lengths) if check_lengths else None
     costs = FusedJointRnnt.apply(enc_out, dec_out, weight, bias, targets, logit_lengths, target_lengths, int(blank),
                                  _lib.ACT_CODES[activation], float(act_param), int(max_chunk_cells))
+    if check is not None:
+        check.finish(T, U, targets.shape[1])  # raises what torchaudio raises; the kernels above are already queued
     return _reduce(costs, reduction)
