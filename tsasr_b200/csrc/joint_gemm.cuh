@@ -644,10 +644,14 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                         const int chunk0 = (col0 & 63) >> 3;  // 0, 2, 4 or 6
                         uint8_t* img = reinterpret_cast<uint8_t*>(p.dY_img) +
                                        ((size_t)(tile - p.tile_begin) * (NT * 4) + vb) * kABlockBytes;
-#pragma unroll
-                        for (int c2 = 0; c2 < 2; ++c2) {
-                            const uint4 o = make_uint4(packed[4 * c2], packed[4 * c2 + 1], packed[4 * c2 + 2], packed[4 * c2 + 3]);
-                            *reinterpret_cast<uint4*>(img + sw128_offset((uint32_t)row, (uint32_t)(chunk0 + c2))) = o;
+                        // the two 16-byte chunks of these 16 columns share one 32-byte sector of the swizzled row
+                        // (chunk0 is even, the XOR with row & 7 only swaps them for odd rows): ONE 256-bit store
+                        {
+                            const bool swap = row & 1;
+                            uint8_t* dst = img + (uint32_t)row * 128u + ((((uint32_t)chunk0 ^ ((uint32_t)row & 7u)) >> 1) << 5);
+                            st_global_v8(dst, swap ? packed[4] : packed[0], swap ? packed[5] : packed[1], swap ? packed[6] : packed[2],
+                                         swap ? packed[7] : packed[3], swap ? packed[0] : packed[4], swap ? packed[1] : packed[5],
+                                         swap ? packed[2] : packed[6], swap ? packed[3] : packed[7]);
                         }
                         // patch the two special columns from the saved lattice (same thread, program order)
                         if (valid) {
