@@ -15,7 +15,7 @@ struct BwdPlan {
     int chunk_tiles;      // multiple of nTu
     int n_chunks;
     int NV2, NHU, NVB, NT4;
-    int hu_blk[3], hu_splits[3], hu_pair0[3], max_splits;
+    int hu_blk[3], hu_splits[3], hu_item0[3], max_splits, dw_pairs;
     size_t dY_bytes, J_bytes, part_bytes, dW_bytes, db_bytes, total;
 };
 
@@ -81,38 +81,57 @@ static void plan_bwd(const JointParams& jp, int num_sms, long long max_chunk_cel
         pl->hu_blk[0] = 0;
         if (KBe <= 6) { pl->NHU = 1; pl->hu_blk[1] = jp.KB; pl->hu_blk[2] = jp.KB; }
         else { pl->NHU = 2; pl->hu_blk[1] = KBe - 2 < 8 ? KBe - 2 : 8; pl->hu_blk[2] = jp.KB; }
-        // split-K factors proportional to the measured cycles per pipeline stage of a unit (config 2, L2-bound:
-        // ~580 + 157 per J half-image slot), so that all units sweep the tiles at the same pace and finish together
+        // Schedule: work items (h-unit, v-tile, split) are dealt round-robin to the CTA pairs, h-unit 0 first.
+        // Item cost ~ measured cycles per pipeline stage of the unit (config 2, L2-bound: ~580 + 157 per J
+        // half-image slot) / split factor.  For k = 1, 2, ... items per pair, pick split factors that fill k *
+        // pairs slots with near-equal items and keep the k with the smallest simulated makespan; a larger k must
+        // promise >= 10 % (measured: at config 2 the model predicted 4 % for k = 2 and it ran 8 % slower; at V = 5000
+        // k = 3 runs 18 % faster than k = 1).
         const int pairs = num_sms / 2;
-        int w[2] = {0, 0}, wsum = 0;
+        int w[2] = {0, 0};
         for (int u = 0; u < pl->NHU; ++u) {
             const int nblk_e = (pl->hu_blk[u + 1] - pl->hu_blk[u] + 1) & ~1;
             w[u] = 580 + 157 * (nblk_e / 2);
         }
         if (const char* env = getenv("TSASR_DEBUG_DW_WEIGHTS")) sscanf(env, "%d,%d", &w[0], &w[1]);  // development knob
-        for (int u = 0; u < pl->NHU; ++u) wsum += w[u];
-        for (int u = 0; u < pl->NHU; ++u) {
-            int sp = pairs * w[u] / (wsum * pl->NV2);
-            pl->hu_splits[u] = sp < 1 ? 1 : sp;
-        }
-        pl->hu_splits[pl->NHU] = 0;
-        for (;;) {  // hand leftover pairs to the most loaded unit
-            int used = 0, worst = 0;
-            for (int u = 0; u < pl->NHU; ++u) {
-                used += pl->hu_splits[u] * pl->NV2;
-                if ((long long)w[u] * pl->hu_splits[worst] > (long long)w[worst] * pl->hu_splits[u]) worst = u;
+        double best_span = 1e30;
+        int best_sp[2] = {1, 1};
+        int k_max = 4;
+        if (const char* env = getenv("TSASR_DEBUG_DW_K")) k_max = atoi(env) >= 1 ? atoi(env) : 4;  // development knob
+        const double drain = 3000.0 / (2.0 * pl->chunk_tiles);  // one accumulator drain, in stage-cost units per tile
+        for (int k = 1; k <= k_max; ++k) {
+            const int slots = k * pairs;
+            int sp[2] = {1, 1};
+            if (pl->NV2 * pl->NHU > slots) continue;
+            for (;;) {  // grow the split factor of the unit type with the most expensive items while slots remain
+                int used = 0, worst = 0;
+                for (int u = 0; u < pl->NHU; ++u) {
+                    used += sp[u] * pl->NV2;
+                    if ((long long)w[u] * sp[worst] > (long long)w[worst] * sp[u]) worst = u;
+                }
+                if (used + pl->NV2 > slots || sp[worst] >= pl->chunk_tiles) break;
+                ++sp[worst];
             }
-            if (used + pl->NV2 > pairs) break;
-            ++pl->hu_splits[worst];
+            // simulate the round-robin deal
+            double span = 0;
+            const int n0 = sp[0] * pl->NV2, n_items = n0 + (pl->NHU > 1 ? sp[1] * pl->NV2 : 0);
+            for (int c = 0; c < pairs && c < n_items; ++c) {
+                double t = 0;
+                for (int it = c; it < n_items; it += pairs) t += it < n0 ? (double)w[0] / sp[0] : (double)w[1] / sp[1];
+                if (t > span) span = t;
+            }
+            span += drain * (k - 1);
+            if (span < best_span * 0.90) { best_span = span; best_sp[0] = sp[0]; best_sp[1] = sp[1]; }
         }
         pl->max_splits = 1;
-        pl->hu_pair0[0] = 0;
-        for (int u = 0; u < pl->NHU; ++u) {
-            if (pl->hu_splits[u] > pl->chunk_tiles) pl->hu_splits[u] = pl->chunk_tiles;
-            pl->hu_pair0[u + 1] = pl->hu_pair0[u] + pl->hu_splits[u] * pl->NV2;
+        pl->hu_item0[0] = 0;
+        pl->hu_splits[2] = 0;
+        for (int u = 0; u < 2; ++u) {
+            pl->hu_splits[u] = u < pl->NHU ? best_sp[u] : 0;
+            pl->hu_item0[u + 1] = pl->hu_item0[u] + pl->hu_splits[u] * pl->NV2;
             if (pl->hu_splits[u] > pl->max_splits) pl->max_splits = pl->hu_splits[u];
         }
-        if (pl->NHU == 1) pl->hu_pair0[2] = pl->hu_pair0[1];
+        pl->dw_pairs = pl->hu_item0[2] < pairs ? pl->hu_item0[2] : pairs;
     }
     pl->dY_bytes = align_up((size_t)pl->chunk_tiles * pl->NT4 * kImgBytes, 1024);
     pl->J_bytes = align_up((size_t)pl->chunk_tiles * jp.KB * kImgBytes, 1024);
@@ -197,7 +216,7 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
     bp.dW_part = reinterpret_cast<float*>(ws + pl.dY_bytes + pl.J_bytes + pl.part_bytes);
     bp.db_part = reinterpret_cast<float*>(ws + pl.dY_bytes + pl.J_bytes + pl.part_bytes + pl.dW_bytes);
     bp.NV2 = pl.NV2; bp.NHU = pl.NHU;
-    for (int i = 0; i < 3; ++i) { bp.hu_blk[i] = pl.hu_blk[i]; bp.hu_pair0[i] = pl.hu_pair0[i]; }
+    for (int i = 0; i < 3; ++i) { bp.hu_blk[i] = pl.hu_blk[i]; bp.hu_item0[i] = pl.hu_item0[i]; }
     bp.hu_splits[0] = pl.hu_splits[0]; bp.hu_splits[1] = pl.hu_splits[1];
     bp.enc = reinterpret_cast<const __nv_bfloat16*>(enc);
     bp.dec = reinterpret_cast<const __nv_bfloat16*>(dec);
@@ -308,7 +327,7 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
         {
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));
-            cfg.gridDim = dim3(2 * pl.hu_pair0[pl.NHU]);
+            cfg.gridDim = dim3(2 * pl.dw_pairs);
             cfg.blockDim = dim3(kBwdThreads);
             cfg.dynamicSmemBytes = dwL.total;
             cfg.stream = st;
@@ -322,7 +341,7 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
             static const bool prof_on = getenv("TSASR_DEBUG_PROF") != nullptr;
             long long* d_prof = nullptr;
             BwdParams bpp = bp;
-            const int n = 2 * pl.hu_pair0[pl.NHU];
+            const int n = 2 * pl.dw_pairs;
             if (prof_on) {
                 cudaMalloc(&d_prof, sizeof(long long) * 4 * n);
                 cudaMemset(d_prof, 0, sizeof(long long) * 4 * n);
@@ -336,13 +355,13 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
                 cudaStreamSynchronize(st);
                 long long* h = new long long[4 * n];
                 cudaMemcpy(h, d_prof, sizeof(long long) * 4 * n, cudaMemcpyDeviceToHost);
-                for (int u = 0; u < pl.NHU; ++u) {
-                    double tot = 0, full = 0, stages = 0;
+                {
+                    double tot = 0, full = 0, stages = 0, mx = 0;
                     int nl = 0;
                     for (int i = 0; i < n; ++i)
-                        if (h[4 * i] > 0 && h[4 * i + 1] == u) { tot += h[4 * i]; full += h[4 * i + 2]; stages += h[4 * i + 3]; ++nl; }
-                    if (nl) fprintf(stderr, "[tsasr prof] dw h-unit %d (blocks %d..%d, %d splits): pairs=%d cycles/pair=%.0f stages/pair=%.0f cycles/stage=%.0f wait full=%.1f%%\n",
-                                    u, pl.hu_blk[u], pl.hu_blk[u + 1], pl.hu_splits[u], nl, tot / nl, stages / nl, tot / stages, 100 * full / tot);
+                        if (h[4 * i] > 0) { tot += h[4 * i]; full += h[4 * i + 2]; stages += h[4 * i + 3]; ++nl; if (h[4 * i] > mx) mx = h[4 * i]; }
+                    if (nl) fprintf(stderr, "[tsasr prof] dw splits=(%d,%d) items=%d pairs=%d: cycles/pair avg=%.0f max=%.0f cycles/stage=%.0f wait full=%.1f%%\n",
+                                    pl.hu_splits[0], pl.hu_splits[1], pl.hu_item0[2], nl, tot / nl, mx, tot / stages, 100 * full / tot);
                 }
                 delete[] h;
                 cudaFree(d_prof);

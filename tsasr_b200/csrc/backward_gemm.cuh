@@ -52,7 +52,7 @@ struct BwdParams {
     int NHU;           // h-units (1 or 2); the last one also carries db
     int hu_blk[3];     // unit u covers h-blocks [hu_blk[u], hu_blk[u+1])
     int hu_splits[2];  // split-K factor of unit u
-    int hu_pair0[3];   // unit u is worked on by CTA pairs [hu_pair0[u], hu_pair0[u+1])
+    int hu_item0[3];   // work items of h-unit u are numbered [hu_item0[u], hu_item0[u+1])
     int accumulate;    // 0: store, 1: read-modify-write (later chunks)
     long long* prof;   // development: MMA-warp cycle counters per CTA (or nullptr)
 };
@@ -377,11 +377,12 @@ reduce_dpre_kernel(const BwdParams p, float* __restrict__ d_enc, float* __restri
 // of the J images, MN-major B).  The accumulator lives in TMEM for the whole kernel (split-K over the tiles of
 // the chunk); a unit is (256 v-rows, h-unit, split).  H is cut into at most two h-units so that the last one
 // leaves room for db: 32 extra accumulator columns fed by a constant "ones" block (db[v] = sum_cells dY[cell, v]).
-// A pipeline stage is HALF a cell tile (64 cells: 8 KB half-images); the ring holds as many stages as fit
-// 192 KB (4 for a 512-column unit, 8 for a 128-column unit: the narrow units need the depth to cover L2 latency).
-static constexpr int kDwMaxStages = 8;
+// A pipeline stage is HALF a cell tile (64 cells: 8 KB half-images), four stages of fixed geometry (narrow units
+// leave part of each stage unused; a deeper ring for them was measured and makes no difference).
+static constexpr int kDwStages = 4;
 static constexpr int kDwHalfImg = kImgBytes / 2;          // rows 0-63 or 64-127 of an operand image
-static constexpr int kDwRingBytes = 24 * kDwHalfImg;      // 192 KB
+static constexpr int kDwStageBytes = 6 * kDwHalfImg;      // 2 dY + up to 4 J half-images
+static constexpr int kDwRingBytes = kDwStages * kDwStageBytes;  // 192 KB
 static constexpr int kDwDbCols = 32;
 
 struct DwSmem { uint32_t stage_off, ones_off, bar_off, tmem_off, total; };
@@ -431,38 +432,56 @@ __device__ __forceinline__ void umma_dw_stage_e(uint32_t d_tmem, uint64_t a_desc
           "r"(has1), "r"(has_db), "r"(db_col) : "memory");
 }
 
+// Work item = (h-unit, v-tile of 256 rows, split-K slice); items are numbered h-unit 0 first.  CTA pair c works
+// on items c, c + #pairs, ... : with one item per pair this is a plain split-K grid (config 2); with several
+// (large V) the host picks the split factors so that every pair's items add up to about the same cost.
+struct DwItem { int hu, vt2, split, n_splits, hb0, nblk, nblk_e, nb0, nb1, n_slots; bool with_db; };
+__device__ __forceinline__ DwItem dw_item(const BwdParams& p, int item) {
+    DwItem it;
+    it.hu = (p.NHU > 1 && item >= p.hu_item0[1]) ? 1 : 0;
+    const int local = item - p.hu_item0[it.hu];
+    it.n_splits = p.hu_splits[it.hu];
+    it.split = local % it.n_splits;
+    it.vt2 = local / it.n_splits;
+    it.hb0 = p.hu_blk[it.hu];
+    it.nblk = p.hu_blk[it.hu + 1] - it.hb0;     // real h-blocks of the unit
+    it.nblk_e = (it.nblk + 1) & ~1;             // even: the pair's CTAs supply equal halves
+    it.nb0 = min(4, it.nblk_e);                 // blocks per MMA (N = 64 * nb)
+    it.nb1 = it.nblk_e - it.nb0;
+    it.n_slots = (it.nb0 >> 1) + (it.nb1 >> 1);  // J half-images per CTA and stage
+    it.with_db = it.hu == p.NHU - 1;
+    return it;
+}
+// J h-block held in shared slot j (= 2 * mma + i) of CTA r: D columns come out in natural h order
+__device__ __forceinline__ int dw_slot_block(const BwdParams& p, const DwItem& it, int r, int j) {
+    const int m = j >> 1, i = j & 1;
+    const int nb = m ? it.nb1 : it.nb0;
+    if (i >= (nb >> 1)) return -1;
+    const int hb = it.hb0 + 4 * m + r * (nb >> 1) + i;
+    return hb < p.KB ? hb : -1;
+}
+
 __global__ void __launch_bounds__(kBwdThreads, 1)
 dw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_j, const BwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const DwSmem L = dw_smem_layout();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
-    uint64_t* full = bars;        // [n_stages]  leader: bytes of both CTAs
-    uint64_t* empty = bars + 8;   // [n_stages]  every CTA
-    uint64_t* acc_full = bars + 16;
+    uint64_t* full = bars;        // [kDwStages]  leader: bytes of both CTAs
+    uint64_t* empty = bars + 8;   // [kDwStages]  every CTA
+    uint64_t* acc_full = bars + 16;   // every CTA: the item's accumulator is complete
+    uint64_t* acc_empty = bars + 17;  // leader: 8 epilogue warps have drained it
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
-
-    // unit = (v-tile of 256 rows, h-unit, split)
-    const int pair = (int)cluster_id_x();
-    const int hu = (p.NHU > 1 && pair >= p.hu_pair0[1]) ? 1 : 0;
-    const int local = pair - p.hu_pair0[hu];
-    const int n_splits = p.hu_splits[hu];
-    const int split = local % n_splits, vt2 = local / n_splits;
-    const int hb0 = p.hu_blk[hu];
-    const int nblk = p.hu_blk[hu + 1] - hb0;      // real h-blocks of the unit
-    const int nblk_e = (nblk + 1) & ~1;           // even: the pair's CTAs supply equal halves
-    const int nb0 = min(4, nblk_e), nb1 = nblk_e - nb0;  // blocks per MMA (N = 64 * nb)
-    const bool with_db = hu == p.NHU - 1;
+    const int pair = (int)cluster_id_x(), n_pairs = (int)num_clusters_x();
     const int n_tiles = p.tile_end - p.tile_begin;
-    const int n_slots = (nb0 >> 1) + (nb1 >> 1);  // J half-images per CTA and stage
-    const uint32_t stage_bytes = (uint32_t)(2 + n_slots) * kDwHalfImg;
-    const uint32_t n_stages = min((uint32_t)kDwMaxStages, kDwRingBytes / stage_bytes);
+    const int n_items = p.hu_item0[p.NHU];
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();
-        for (uint32_t i = 0; i < n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kDwStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 8);
         fence_barrier_init();
     }
     // constant "ones" B block (leader: column 0 = 1.0 for all 64 cells; partner: zeros)
@@ -481,46 +500,37 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constan
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
-    // J h-block held in shared slot j (= 2 * mma + i) of CTA r: D columns come out in natural h order
-    auto slot_block = [&](int r, int j) -> int {
-        const int m = j >> 1, i = j & 1;
-        const int nb = m ? nb1 : nb0;
-        if (i >= (nb >> 1)) return -1;
-        const int hb = hb0 + 4 * m + r * (nb >> 1) + i;
-        return hb < p.KB ? hb : -1;
-    };
-
     if (warp_idx == kBwdWarpLoad) {
         uint32_t stage = 0, phase = 0;
         const uint32_t full0 = mapa_u32(smem_u32(&full[0]), 0);
-        int nB[2] = {0, 0};
-        for (int r = 0; r < 2; ++r)
-            for (int j = 0; j < 4; ++j) nB[r] += slot_block(r, j) >= 0;
-        const uint32_t bytes_pair = (uint32_t)(4 + nB[0] + nB[1]) * kDwHalfImg;
-        for (int tl = split; tl < n_tiles; tl += n_splits) {
-            if (!tile_live(p, p.tile_begin + tl)) continue;
-            const int dy_row0 = (tl * p.NT4 + vt2 * 4 + rank * 2) * 128;
-            for (int half = 0; half < 2; ++half) {
-                mbar_wait(&empty[stage], phase ^ 1, 0xB00 | stage);
-                __syncwarp();
-                uint8_t* st = smem + L.stage_off + stage * stage_bytes;
-                if (rank == 0) mbar_arrive_expect_tx_e(&full[stage], bytes_pair);
-                tma_load_2d_2cta_e(st, &tmap_dy, full0 + stage * 8, 0, dy_row0 + half * 64);
-                tma_load_2d_2cta_e(st + kDwHalfImg, &tmap_dy, full0 + stage * 8, 0, dy_row0 + 128 + half * 64);
+        for (int item = pair; item < n_items; item += n_pairs) {
+            const DwItem it = dw_item(p, item);
+            int nB = 0;
+            for (int r = 0; r < 2; ++r)
+                for (int j = 0; j < 4; ++j) nB += dw_slot_block(p, it, r, j) >= 0;
+            const uint32_t bytes_pair = (uint32_t)(4 + nB) * kDwHalfImg;
+            for (int tl = it.split; tl < n_tiles; tl += it.n_splits) {
+                if (!tile_live(p, p.tile_begin + tl)) continue;
+                const int dy_row0 = (tl * p.NT4 + it.vt2 * 4 + rank * 2) * 128;
+                for (int half = 0; half < 2; ++half) {
+                    mbar_wait(&empty[stage], phase ^ 1, 0xB00 | stage);
+                    __syncwarp();
+                    uint8_t* st = smem + L.stage_off + stage * kDwStageBytes;
+                    if (rank == 0) mbar_arrive_expect_tx_e(&full[stage], bytes_pair);
+                    tma_load_2d_2cta_e(st, &tmap_dy, full0 + stage * 8, 0, dy_row0 + half * 64);
+                    tma_load_2d_2cta_e(st + kDwHalfImg, &tmap_dy, full0 + stage * 8, 0, dy_row0 + 128 + half * 64);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int hb = slot_block(rank, j);
-                    if (hb >= 0) tma_load_2d_2cta_e(st + (2 + j) * kDwHalfImg, &tmap_j, full0 + stage * 8, 0, (tl * p.KB + hb) * 128 + half * 64);
+                    for (int j = 0; j < 4; ++j) {
+                        const int hb = dw_slot_block(p, it, rank, j);
+                        if (hb >= 0) tma_load_2d_2cta_e(st + (2 + j) * kDwHalfImg, &tmap_j, full0 + stage * 8, 0, (tl * p.KB + hb) * 128 + half * 64);
+                    }
+                    if (++stage == kDwStages) { stage = 0; phase ^= 1; }
                 }
-                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp_idx == kBwdWarpMma) {
         if (rank == 0) {  // whole warp, converged
-            uint32_t stage = 0, phase = 0;
-            bool first = true;
-            const uint32_t idesc0 = make_idesc_bf16(256, nb0 * 64, 1, 1);
-            const uint32_t idesc1 = make_idesc_bf16(256, nb1 > 0 ? nb1 * 64 : 64, 1, 1);
+            uint32_t stage = 0, phase = 0, n_done = 0;
             const uint32_t idesc_db = make_idesc_bf16(256, kDwDbCols, 1, 1);
             // MN-major operands: 64-wide blocks kDwHalfImg apart, 8-row K groups 1024 B apart; a k-step is 16 rows
             const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smem + L.stage_off), kDwHalfImg, 1024);
@@ -528,72 +538,99 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constan
             const uint64_t o_desc0 = make_smem_desc_sw128(smem_u32(smem + L.ones_off), kDwHalfImg, 1024);
             long long t_full = 0, tm = 0, n_st = 0;
             const long long t_begin = clock64();
-            for (int tl = split; tl < n_tiles; tl += n_splits) {
-                if (!tile_live(p, p.tile_begin + tl)) continue;
-                for (int half = 0; half < 2; ++half) {
-                    if (p.prof) tm = clock64();
-                    mbar_wait(&full[stage], phase, 0xC00 | stage);
-                    if (p.prof) { t_full += clock64() - tm; ++n_st; }
-                    tcgen05_fence_after();
-                    // 4 k-steps x (dW columns 0-255, dW columns 256-511, db) in one issue block
-                    const uint32_t off = stage * (stage_bytes >> 4);
-                    umma_dw_stage_e(tmem_base, a_desc0 + off, b_desc0 + off, o_desc0, idesc0, idesc1, idesc_db, !first,
-                                    nb1 > 0, with_db, nblk_e * 64);
-                    first = false;
-                    umma_commit_2cta_e(&empty[stage], 3);
-                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
+            for (int item = pair; item < n_items; item += n_pairs) {
+                const DwItem it = dw_item(p, item);
+                const uint32_t idesc0 = make_idesc_bf16(256, it.nb0 * 64, 1, 1);
+                const uint32_t idesc1 = make_idesc_bf16(256, it.nb1 > 0 ? it.nb1 * 64 : 64, 1, 1);
+                bool first = true;
+                for (int tl = it.split; tl < n_tiles; tl += it.n_splits) {
+                    if (!tile_live(p, p.tile_begin + tl)) continue;
+                    if (first) {  // the previous item's accumulator must have been drained by both CTAs
+                        mbar_wait(acc_empty, (n_done & 1) ^ 1, 0xC80);
+                        tcgen05_fence_after();
+                    }
+                    for (int half = 0; half < 2; ++half) {
+                        if (p.prof) tm = clock64();
+                        mbar_wait(&full[stage], phase, 0xC00 | stage);
+                        if (p.prof) { t_full += clock64() - tm; ++n_st; }
+                        tcgen05_fence_after();
+                        // 4 k-steps x (dW columns 0-255, dW columns 256-511, db) in one issue block
+                        const uint32_t off = stage * (kDwStageBytes >> 4);
+                        umma_dw_stage_e(tmem_base, a_desc0 + off, b_desc0 + off, o_desc0, idesc0, idesc1, idesc_db, !first,
+                                        it.nb1 > 0, it.with_db, it.nblk_e * 64);
+                        first = false;
+                        umma_commit_2cta_e(&empty[stage], 3);
+                        if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+                if (!first) {  // at least one live tile: hand the accumulator to the epilogues
+                    umma_commit_2cta_e(acc_full, 3);
+                    ++n_done;
                 }
             }
-            umma_commit_2cta_e(acc_full, 3);
             if (p.prof && lane == 0) {
                 long long* o = p.prof + blockIdx.x * 4;
-                o[0] = clock64() - t_begin; o[1] = hu; o[2] = t_full; o[3] = n_st;
+                o[0] = clock64() - t_begin; o[1] = 0; o[2] = t_full; o[3] = n_st;
             }
         }
     } else {
         const int q = warp_idx & 3;
         const int row = q * 32 + lane;
-        const int v = vt2 * 256 + rank * 128 + row;
-        // did this split see any live tile?  (all roles agree; the epilogue must not wait otherwise)
-        bool any = false;
-        for (int tl = split; tl < n_tiles; tl += n_splits) any |= tile_live(p, p.tile_begin + tl);
+        const uint32_t acc_empty_leader = mapa_u32(smem_u32(acc_empty), 0);
         const size_t vrows = (size_t)p.NV2 * 256;
-        float* wrow = p.dW_part + ((size_t)split * vrows + v) * p.H + hb0 * 64;
-        if (any) {
-            mbar_wait(acc_full, 0, 0xD00);
-            tcgen05_fence_after();
-        }
-        for (int cc = 0; cc < nblk * 64; cc += 32) {
-            uint32_t raw[32];
+        uint32_t n_done = 0;
+        for (int item = pair; item < n_items; item += n_pairs) {
+            const DwItem it = dw_item(p, item);
+            const int v = it.vt2 * 256 + rank * 128 + row;
+            // did this split see any live tile?  (all roles agree; the epilogue must not wait otherwise)
+            bool any = false;
+            for (int tl = it.split; tl < n_tiles; tl += it.n_splits) any |= tile_live(p, p.tile_begin + tl);
+            float* wrow = p.dW_part + ((size_t)it.split * vrows + v) * p.H + it.hb0 * 64;
             if (any) {
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + cc, raw);
-                tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) raw[j] = 0u;
+                mbar_wait(acc_full, n_done & 1, 0xD00);
+                tcgen05_fence_after();
             }
-            float4* dst = reinterpret_cast<float4*>(wrow + cc);
+            for (int cc = 0; cc < it.nblk * 64; cc += 32) {
+                uint32_t raw[32];
+                if (any) {
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + cc, raw);
+                    tmem_ld_wait();
+                } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 x = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
-                                       __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
-                if (p.accumulate) {
-                    const float4 o = dst[j];
-                    x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
+                    for (int j = 0; j < 32; ++j) raw[j] = 0u;
                 }
-                dst[j] = x;
+                float4* dst = reinterpret_cast<float4*>(wrow + cc);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 x = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                           __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+                    if (p.accumulate) {
+                        const float4 o = dst[j];
+                        x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
+                    }
+                    dst[j] = x;
+                }
             }
-        }
-        if (with_db) {
-            uint32_t raw[16];
-            float x = 0.f;
-            if (any) {
-                tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + nblk_e * 64, raw);
-                tmem_ld_wait();
-                x = __uint_as_float(raw[0]);
+            if (it.with_db) {
+                uint32_t raw[16];
+                float x = 0.f;
+                if (any) {
+                    tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + it.nblk_e * 64, raw);
+                    tmem_ld_wait();
+                    x = __uint_as_float(raw[0]);
+                }
+                float* d = p.db_part + (size_t)it.split * vrows + v;
+                *d = p.accumulate ? *d + x : x;
             }
-            float* d = p.db_part + (size_t)split * vrows + v;
-            *d = p.accumulate ? *d + x : x;
+            if (any) {  // the accumulator may be overwritten by the pair's next item
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (rank) mbar_arrive_cluster(acc_empty_leader);
+                    else mbar_arrive(acc_empty);
+                }
+                ++n_done;
+            }
         }
     }
     tcgen05_fence_before();

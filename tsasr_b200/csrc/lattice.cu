@@ -51,6 +51,34 @@ __device__ __forceinline__ void stg_stream_f4(float4* p, const float4& v) {
                  : "memory");
 }
 
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_u4(uint4* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+// 8 half-precision values of one 16-byte word <-> 8 floats
+template <typename T>
+__device__ __forceinline__ void unpack8(const uint4& w, float* x) {
+    const T* h = reinterpret_cast<const T*>(&w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = to_float<T>(h[i]);
+}
+template <typename T>
+__device__ __forceinline__ uint4 pack8(const float* x) {
+    uint4 w;
+    T* h = reinterpret_cast<T*>(&w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = from_float<T>(x[i]);
+    return w;
+}
+
 // online (max, sum) update with a block of values already in registers
 __device__ __forceinline__ void online_update(float& m, float& s, const float* x, int n) {
     float cm = x[0];
@@ -117,6 +145,26 @@ logits_to_lattice_kernel(const T* __restrict__ logits, const int* __restrict__ t
                         n = 4 * j + 4;
                     } else {
                         x[4 * j + 0] = x[4 * j + 1] = x[4 * j + 2] = x[4 * j + 3] = -INFINITY;
+                    }
+                }
+                if (n > 0) online_update(m, s, x, 32);
+            }
+        } else if (sizeof(T) == 2 && (V & 7) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0)) {
+            // half-precision rows: 16-byte streaming loads, 8 values each
+            const uint4* row8 = reinterpret_cast<const uint4*>(row);
+            const int V8 = V >> 3;
+            for (int base = 0; base < V8; base += 32 * 4) {
+                float x[32];
+                int n = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int idx = base + j * 32 + lane;
+                    if (idx < V8) {
+                        unpack8<T>(ldg_stream_u4(row8 + idx), x + 8 * j);
+                        n = 8 * j + 8;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) x[8 * j + i] = -INFINITY;
                     }
                 }
                 if (n > 0) online_update(m, s, x, 32);
@@ -308,10 +356,15 @@ logits_grad_kernel(const T* __restrict__ logits, const int* __restrict__ targets
     T* out = dlogits + (size_t)cell * V;
     const bool vec = sizeof(T) == 4 && (V & 3) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const bool vec8 = sizeof(T) == 2 && (V & 7) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     if (t >= Tb || u >= Ub) {
         if (vec) {
             float4* o4 = reinterpret_cast<float4*>(out);
             for (int i = lane; i < (V >> 2); i += 32) stg_stream_f4(o4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        } else if (vec8) {
+            uint4* o8 = reinterpret_cast<uint4*>(out);
+            for (int i = lane; i < (V >> 3); i += 32) stg_stream_u4(o8 + i, make_uint4(0u, 0u, 0u, 0u));
         } else {
             for (int i = lane; i < V; i += 32) out[i] = from_float<T>(0.f);
         }
@@ -349,6 +402,29 @@ logits_grad_kernel(const T* __restrict__ logits, const int* __restrict__ targets
                     g.z = grad(x[j].z, 4 * idx + 2);
                     g.w = grad(x[j].w, 4 * idx + 3);
                     stg_stream_f4(o4 + idx, g);
+                }
+            }
+        }
+    } else if (vec8) {
+        const uint4* r8 = reinterpret_cast<const uint4*>(row);
+        uint4* o8 = reinterpret_cast<uint4*>(out);
+        const int V8 = V >> 3;
+        for (int base = 0; base < V8; base += 32 * 4) {
+            uint4 w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = base + j * 32 + lane;
+                if (idx < V8) w[j] = ldg_stream_u4(r8 + idx);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = base + j * 32 + lane;
+                if (idx < V8) {
+                    float x[8];
+                    unpack8<T>(w[j], x);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[i] = grad(x[i], 8 * idx + i);
+                    stg_stream_u4(o8 + idx, pack8<T>(x));
                 }
             }
         }
