@@ -112,6 +112,20 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
                     size_t workspace_bytes, long long max_chunk_cells, float* d_enc, float* d_dec, float* dW,
                     float* db, tsasr_stream_t stream);
 
+/* ---- decode-time joint step (greedy / beam search) ------------------------------------------------
+ * Replaces TransducerBeamSearcher._joint_forward_step (SB/decoders/transducer.py:375-384): Transducer_joint
+ * on [B,1,1,H] inputs + the classifier Linear + LogSoftmax, two small launches instead of five.
+ *   enc_t fp32 [B,H] (frame t of every hypothesis), dec fp32 [B,H]: rows of H contiguous floats, *_row_stride
+ *   elements apart (a strided view of the encoder output needs no copy; 0 broadcasts one row over B);
+ *   W fp32 [V,H], bias fp32 [V] or NULL;  out: log_probs fp32 [B,V].  fp32 arithmetic on the same operands as
+ *   the eager path.
+ * The workspace (tsasr_joint_decode_workspace_bytes(V) bytes, 16-byte aligned) is scratch for per-CTA softmax
+ * partials and may be reused by later calls on the same stream. */
+size_t tsasr_joint_decode_workspace_bytes(int V);
+int tsasr_joint_decode_step(const float* enc_t, const float* dec, long long enc_row_stride, long long dec_row_stride,
+                            const float* W, const float* bias, int B, int H, int V, int act_kind, float act_param,
+                            float* log_probs, void* workspace, size_t workspace_bytes, tsasr_stream_t stream);
+
 /* Test-only: dump the logits tile-wise recomputed by the tcgen05 mainloop into a dense fp32
  * [B,T,U,V] buffer (small shapes), so the GEMM can be checked in isolation. */
 int tsasr_joint_debug_logits(const void* enc, const void* dec, const void* W, const float* bias, int B, int T, int U,

@@ -1,0 +1,106 @@
+"""Decode-time joint step: the fused kernel behind
+``TransducerBeamSearcher._joint_forward_step`` (SB/decoders/transducer.py:375-384).
+
+Oracle: the reference's eager chain (oracle/greedy_decode.py restates the searcher's greedy loop); golden vectors
+come from the REAL searcher class run in the authoring container (oracle/make_golden_decode.py).
+Tolerance: fp32 arithmetic on both sides, log-probs within 2e-5 absolute; decoded label sequences bit-exact."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import tsasr_b200
+from tsasr_b200 import decode
+from oracle.greedy_decode import ToyPredictor, eager_joint_step, greedy_decode
+
+
+def _golden_modules(g, device):
+    B, T, V, E, HID, H = (int(x) for x in g["dims"])
+    pred = ToyPredictor(V, E, HID, H)
+    pred.load_state_dict({k[5:]: torch.tensor(g[k]) for k in g if k.startswith("pred.")})
+    head = torch.nn.Linear(H, V)
+    with torch.no_grad():
+        head.weight.copy_(torch.tensor(g["W"]))
+        head.bias.copy_(torch.tensor(g["b"]))
+    tjoint = tsasr_b200.Transducer_joint(joint="sum", nonlinearity=torch.nn.LeakyReLU)
+    hyps, o = [], 0
+    for n in g["hyp_lens"]:
+        hyps.append([int(x) for x in g["hyp_flat"][o:o + int(n)]])
+        o += int(n)
+    return pred.to(device).eval(), head.to(device).eval(), tjoint, torch.tensor(g["tn"]).to(device), hyps
+
+
+def test_oracle_greedy_loop_reproduces_reference_searcher(golden):
+    """CPU: the restated loop with the eager step gives exactly the hypotheses of the reference's searcher class."""
+    g = golden("greedy_decode")
+    pred, head, tjoint, tn, hyps = _golden_modules(g, "cpu")
+    got, scores = greedy_decode(tn, pred.layers(), eager_joint_step(tjoint, [head], torch.nn.LogSoftmax(dim=-1)))
+    assert got == hyps
+    np.testing.assert_allclose(np.exp(np.array(scores)).mean(), float(g["mean_exp_score"]), rtol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,V,act", [(1, 640, 1000, "leaky_relu"), (16, 640, 1000, "leaky_relu"), (5, 64, 29, "tanh"),
+                                       (40, 256, 5003, "relu"), (3, 128, 7, "identity")])
+def test_decode_step_vs_eager_chain(B, H, V, act):
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(B * 1000 + V)
+    enc = torch.randn(B, H, generator=g).to(d)
+    dec = torch.randn(B, H, generator=g).to(d)
+    W = (torch.randn(V, H, generator=g) / H ** 0.5 * 3).to(d)
+    b = torch.randn(V, generator=g).to(d)
+    got = decode.joint_decode_step(enc, dec, W, b, act, 0.01)
+    f = {"leaky_relu": lambda x: torch.nn.functional.leaky_relu(x, 0.01), "relu": torch.relu, "tanh": torch.tanh,
+         "identity": lambda x: x}[act]
+    ref = torch.log_softmax(torch.nn.functional.linear(f(enc.double() + dec.double()), W.double(), b.double()), dim=-1)
+    assert (got.double() - ref).abs().max().item() < 2e-5
+    top2 = ref.topk(2, dim=-1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-4           # arg-max must agree wherever it is not a numerical tie
+    assert torch.equal(got.argmax(-1)[clear], ref.argmax(-1)[clear])
+    np.testing.assert_allclose(got.exp().sum(-1).cpu().numpy(), 1.0, rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_greedy_decode_with_fused_step_vs_reference_golden(golden):
+    g = golden("greedy_decode")
+    d = torch.device("cuda:0")
+    pred, head, tjoint, tn, hyps = _golden_modules(g, d)
+    softmax = torch.nn.LogSoftmax(dim=-1)
+    step = decode.fused_joint_forward_step(tjoint, [head], softmax)
+    assert step is not None
+    torch.backends.cudnn.allow_tf32 = False  # the toy LSTM must run in fp32 like the CPU run that made the vector
+    launches0 = tsasr_b200._lib.launch_count()
+    got, scores = greedy_decode(tn, pred.layers(), step)
+    assert tsasr_b200._lib.launch_count() - launches0 == 2 * tn.shape[1]   # logits + normalise kernel per decoded frame
+    assert got == hyps
+    np.testing.assert_allclose(np.exp(np.array(scores)).mean(), float(g["mean_exp_score"]), rtol=1e-4)
+    # the first frames' full log-prob rows, as produced by the reference's own _joint_forward_step
+    with torch.no_grad():
+        cpu_pred = _golden_modules(g, "cpu")[0]  # prediction-network output computed on CPU, as in the golden run
+        out_pn = cpu_pred.dec_lin(cpu_pred.dec(cpu_pred.emb(torch.zeros(tn.shape[0], 1, dtype=torch.int32)))[0]).to(d)
+        for t in range(g["first_frames_logp"].shape[0]):
+            lp = step(tn[:, t, :].unsqueeze(1).unsqueeze(1), out_pn.unsqueeze(1))
+            assert lp.shape == (tn.shape[0], 1, 1, head.weight.shape[0])
+            np.testing.assert_allclose(lp.squeeze(1).squeeze(1).cpu().numpy(), g["first_frames_logp"][t], atol=2e-5)
+
+
+@pytest.mark.gpu
+def test_patch_searcher_swaps_only_supported_chains():
+    d = torch.device("cuda:0")
+    H, V = 64, 30
+    head = torch.nn.Linear(H, V).to(d)
+    sb_like_head = types.SimpleNamespace(w=head)  # SpeechBrain's Linear keeps nn.Linear in .w (linear.py:61)
+    searcher = types.SimpleNamespace(tjoint=tsasr_b200.Transducer_joint(joint="sum"), classifier_network=[sb_like_head],
+                                     softmax=torch.nn.LogSoftmax(dim=-1))
+    assert decode.patch_searcher(searcher)
+    lp = searcher._joint_forward_step(torch.randn(4, 1, 1, H, device=d), torch.randn(4, 1, 1, H, device=d))
+    assert lp.shape == (4, 1, 1, V) and torch.allclose(lp.exp().sum(-1), torch.ones(4, 1, 1, device=d), atol=1e-5)
+    lp1 = searcher._joint_forward_step(torch.randn(1, 1, 1, H, device=d), torch.randn(1, 1, 1, H, device=d))  # beam search shape
+    assert lp1.shape == (1, 1, 1, V)
+    concat = types.SimpleNamespace(tjoint=tsasr_b200.Transducer_joint(joint="concat"), classifier_network=[head],
+                                   softmax=torch.nn.LogSoftmax(dim=-1))
+    assert not decode.patch_searcher(concat)
+    two_layers = types.SimpleNamespace(tjoint=tsasr_b200.Transducer_joint(joint="sum"), classifier_network=[head, head],
+                                       softmax=torch.nn.LogSoftmax(dim=-1))
+    assert not decode.patch_searcher(two_layers)

@@ -29,6 +29,10 @@ cudaError_t launch_logits_grad(const void*, int, const int*, const int*, const i
                                float, void*, cudaStream_t);
 cudaError_t launch_logprobs_grad(const int*, const int*, const int*, int, int, int, int, int, const float2*,
                                  const float*, const float*, const float*, const float*, float*, cudaStream_t);
+// decode.cu
+cudaError_t launch_joint_decode_step(const float*, const float*, long long, long long, const float*, const float*, int, int, int,
+                                     int, float, float*, void*, cudaStream_t);
+size_t joint_decode_workspace_bytes(int V);
 }  // namespace tsasr
 
 using namespace tsasr;
@@ -387,6 +391,30 @@ int tsasr_joint_fwd(const void* enc, const void* dec, const void* W, const float
     if (int rc = make_joint_maps(&maps, p, enc, dec, W)) return rc;
     ScopedTiming tm("joint_gemm_kernel<FWD>", static_cast<cudaStream_t>(stream));
     return launch_joint<MODE_FWD>(maps, p, sms, static_cast<cudaStream_t>(stream));
+}
+
+size_t tsasr_joint_decode_workspace_bytes(int V) { return V >= 1 ? joint_decode_workspace_bytes(V) : 0; }
+
+int tsasr_joint_decode_step(const float* enc_t, const float* dec, long long enc_row_stride, long long dec_row_stride,
+                            const float* W, const float* bias, int B, int H, int V, int act_kind, float act_param,
+                            float* log_probs, void* workspace, size_t workspace_bytes, tsasr_stream_t stream) {
+    REQUIRE(B >= 1 && H >= 4 && V >= 1, "B, V must be >= 1 and H >= 4 (got %d %d %d)", B, H, V);
+    REQUIRE(H % 4 == 0, "decode step needs H %% 4 == 0 (got %d)", H);
+    REQUIRE(H <= 1536, "decode step supports H <= 1536 (got %d)", H);
+    REQUIRE(enc_t && dec && W && log_probs && workspace, "null pointer argument");
+    REQUIRE(act_kind >= 0 && act_kind <= 3, "unknown activation code %d", act_kind);
+    REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+            "W and workspace must be 16-byte aligned");
+    if (workspace_bytes < joint_decode_workspace_bytes(V))
+        return fail(TSASR_E_WORKSPACE, "workspace too small: need %zu bytes, got %zu", joint_decode_workspace_bytes(V), workspace_bytes);
+    int sms, max_smem;
+    if (int rc = device_info(&sms, &max_smem)) return rc;
+    ScopedTiming tm("joint_decode_step", static_cast<cudaStream_t>(stream));
+    REQUIRE(enc_row_stride >= 0 && dec_row_stride >= 0, "row strides must be >= 0 (0 = broadcast one row over B)");
+    cudaError_t e = launch_joint_decode_step(enc_t, dec, enc_row_stride, dec_row_stride, W, bias, B, H, V, act_kind, act_param,
+                                             log_probs, workspace, static_cast<cudaStream_t>(stream));
+    g_launches += 2 * ((B + 31) / 32);
+    return e == cudaSuccess ? TSASR_OK : cuda_fail(e, "joint_decode_step kernels");
 }
 
 int tsasr_joint_debug_logits(const void* enc, const void* dec, const void* W, const float* bias, int B, int T, int U,

@@ -1,0 +1,113 @@
+"""Decode-time joint step (the other caller of the joint + head modules).
+
+The reference searchers call ``self._joint_forward_step(h_i, out_PN)`` once per decoded frame and hypothesis
+batch (vendor/speechbrain/speechbrain/decoders/transducer.py:177-180, 303-309; definition :375-384):
+``tjoint`` on [B,1,1,H] inputs, the classifier Linear(s) and ``LogSoftmax`` -- five tiny launches.
+``joint_decode_step`` does the same arithmetic (fp32, same operands) in two small launches (csrc/decode.cu);
+``patch_searcher`` swaps it into an existing ``TransducerBeamSearcher`` without touching its search logic.
+"""
+import ctypes
+import types
+
+import torch
+
+from . import _lib
+from .transducer_joint import activation_code
+
+_workspaces = {}
+
+
+def _workspace(dev, V):
+    key = (dev, V)
+    ws = _workspaces.get(key)
+    if ws is None:
+        n = int(_lib.load().tsasr_joint_decode_workspace_bytes(int(V)))
+        ws = _workspaces[key] = torch.empty((max(n, 16),), dtype=torch.uint8, device=dev)
+    return ws
+
+
+def _rows(x, H):
+    """(tensor keeping the storage alive, row stride in elements, rows) for a [..., H] fp32 view whose last dim is
+    contiguous and whose leading dims collapse to one stride; anything else is copied."""
+    if x.dtype == torch.float32 and x.stride(-1) == 1:
+        lead = [(n, s) for n, s in zip(x.shape[:-1], x.stride()[:-1]) if n != 1]
+        if not lead:
+            return x, 0, 1
+        if len(lead) == 1:
+            return x, lead[0][1], lead[0][0]
+    x = x.reshape(-1, H).to(torch.float32).contiguous()
+    return x, H, x.shape[0]
+
+
+def joint_decode_step(enc_t, dec, weight, bias=None, activation="leaky_relu", act_param=0.01):
+    """log_softmax(act(enc_t + dec) @ weight.T + bias) for B hypotheses.
+
+    enc_t, dec : [B, H] or [B,1,1,H] fp32 (strided views are read in place; a single row broadcasts over B)
+    weight     : [V, H] fp32, bias : [V] fp32 or None  ->  log-probs [B, V] fp32
+    """
+    if not (enc_t.is_cuda and dec.is_cuda and weight.is_cuda):
+        raise ValueError("tsasr_b200 needs CUDA tensors; there is no CPU path")
+    V, H = weight.shape
+    e, es, eb = _rows(enc_t, H)
+    d, ds, db = _rows(dec, H)
+    B = max(eb, db)
+    if (eb != B and eb != 1) or (db != B and db != 1):
+        raise ValueError(f"cannot broadcast {tuple(enc_t.shape)} with {tuple(dec.shape)}")
+    if eb == 1:
+        es = 0
+    if db == 1:
+        ds = 0
+    w = weight if (weight.dtype == torch.float32 and weight.is_contiguous()) else weight.detach().to(torch.float32).contiguous()
+    b = bias
+    if b is not None and not (b.dtype == torch.float32 and b.is_contiguous()):
+        b = b.detach().to(torch.float32).contiguous()
+    dev = w.device
+    out = torch.empty((B, V), dtype=torch.float32, device=dev)
+    ws = _workspace(dev, V)
+    code = _lib.ACT_CODES[activation] if isinstance(activation, str) else int(activation)
+    rc = _lib.load().tsasr_joint_decode_step(
+        e.data_ptr(), d.data_ptr(), es, ds, w.data_ptr(), b.data_ptr() if b is not None else None, B, H, V, code,
+        float(act_param), out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
+    if rc != 0:
+        _lib.check(rc)
+    return out
+
+
+def _head_linear(classifier_network):
+    """The single Linear of ``classifier_network`` (SpeechBrain ``Linear`` keeps it in ``.w``), else None."""
+    if len(classifier_network) != 1:
+        return None
+    layer = classifier_network[0]
+    lin = getattr(layer, "w", layer)
+    return lin if isinstance(lin, torch.nn.Linear) else None
+
+
+def fused_joint_forward_step(tjoint, classifier_network, softmax):
+    """Callable with the signature and result of ``_joint_forward_step`` (transducer.py:375-384), or None when the
+    searcher's modules are not the (sum joint, one Linear, LogSoftmax over the last dim) chain the kernel implements."""
+    act = activation_code(getattr(tjoint, "nonlinearity", None))
+    lin = _head_linear(classifier_network)
+    ok_softmax = isinstance(softmax, torch.nn.LogSoftmax) and softmax.dim in (-1, 3)
+    if getattr(tjoint, "joint", None) != "sum" or act is None or lin is None or not ok_softmax:
+        return None
+
+    def step(h_i, out_PN):
+        with torch.no_grad():
+            if not (h_i.is_cuda and lin.weight.is_cuda) or lin.weight.shape[1] % 4 != 0:
+                out = tjoint(h_i, out_PN)
+                for layer in classifier_network:
+                    out = layer(out)
+                return softmax(out)
+            lp = joint_decode_step(h_i, out_PN, lin.weight, lin.bias, act[0], act[1])
+            return lp.view(lp.shape[0], 1, 1, lp.shape[1]) if h_i.dim() == 4 else lp
+
+    return step
+
+
+def patch_searcher(searcher):
+    """Replace ``searcher._joint_forward_step`` by the fused step (returns True when patched)."""
+    step = fused_joint_forward_step(searcher.tjoint, searcher.classifier_network, searcher.softmax)
+    if step is None:
+        return False
+    searcher._joint_forward_step = types.MethodType(lambda self, h_i, out_PN: step(h_i, out_PN), searcher)
+    return True
