@@ -112,6 +112,18 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
                     size_t workspace_bytes, long long max_chunk_cells, float* d_enc, float* d_dec, float* dW,
                     float* db, tsasr_stream_t stream);
 
+/* ---- host-path helpers of the fused loss (one launch each instead of a dozen elementwise launches) -------
+ * tsasr_prepare_lengths: the integer length conversion of SB/nnet/losses.py:58-59, bit-exact
+ * ((rel * dim) in fp32, round-half-to-even, int32) for both vectors -- pass rel_* = NULL and abs_* instead when the
+ * lengths are already absolute -- plus stats_out[4] = {max T_b, max labels, min T_b, min labels}, the numbers
+ * torchaudio's argument checks compare against the tensor shapes.  *_out may be NULL with abs_* inputs. */
+int tsasr_prepare_lengths(const float* rel_logit_lengths, const float* rel_target_lengths, const int32_t* abs_logit_lengths,
+                          const int32_t* abs_target_lengths, int B, int T, int n_targets, int32_t* logit_lengths_out,
+                          int32_t* target_lengths_out, int32_t* stats_out, tsasr_stream_t stream);
+/* fp32 -> bf16 (round to nearest even) of the three GEMM operands in one launch; counts are in elements. */
+int tsasr_cast_operands_bf16(const float* enc, size_t n_enc, const float* dec, size_t n_dec, const float* W, size_t n_w,
+                             void* enc16, void* dec16, void* W16, tsasr_stream_t stream);
+
 /* ---- decode-time joint step (greedy / beam search) ------------------------------------------------
  * Replaces TransducerBeamSearcher._joint_forward_step (SB/decoders/transducer.py:375-384): Transducer_joint
  * on [B,1,1,H] inputs + the classifier Linear + LogSoftmax, two small launches instead of five.

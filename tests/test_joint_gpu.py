@@ -241,3 +241,25 @@ def test_fused_length_precondition_errors_are_raised_after_safe_launch():
     costs = call(ll, tl)  # a valid call afterwards: finite, matches the reference
     ref = reference_joint_loss_fwd_bwd(enc, dec, W, b, targets, ll, tl, 0, "leaky_relu", 0.01, round_bf16=True)
     np.testing.assert_allclose(costs.cpu().numpy(), ref["costs"].numpy(), rtol=LOSS_RTOL)
+
+
+def test_relative_length_conversion_kernel_is_bit_exact():
+    """tsasr_prepare_lengths vs the reference expression of SB/nnet/losses.py:58-59 on half-way and random values:
+    integer results must be identical (round-half-to-even of the fp32 product), statistics included."""
+    from tsasr_b200.functional import _prepare_lengths
+
+    d = _dev()
+    g = torch.Generator().manual_seed(0)
+    for T, n_tg in ((400, 99), (750, 199), (37, 6), (1, 1), (2, 7)):
+        halves = (torch.arange(0, 2 * T + 1, dtype=torch.float32) / (2.0 * T))          # k / 2T: exact .5 products
+        rel_l = torch.cat([halves, torch.rand(3000, generator=g), torch.tensor([1.0, 0.0, 1e-8, 0.99999994])])
+        rel_t = torch.rand(rel_l.shape[0], generator=g)
+        rel_t[: min(len(halves), 2 * n_tg + 1)] = (torch.arange(0, 2 * n_tg + 1, dtype=torch.float32) / (2.0 * n_tg))[: len(halves)]
+        want_l = (rel_l * T).round().int()
+        want_t = (rel_t * n_tg).round().int()
+        ll, tl, stats, _ = _prepare_lengths(rel_l.to(d), rel_t.to(d), T, n_tg, relative=True)
+        torch.cuda.synchronize()
+        assert torch.equal(ll.cpu(), want_l) and torch.equal(tl.cpu(), want_t)
+        assert stats.cpu().tolist() == [int(want_l.max()), int(want_t.max()), int(want_l.min()), int(want_t.min())]
+        ll2, tl2, stats2, _ = _prepare_lengths(want_l.to(d), want_t.to(d), T, n_tg, relative=False)
+        assert torch.equal(ll2.cpu(), want_l) and stats2.cpu().tolist() == stats.cpu().tolist()

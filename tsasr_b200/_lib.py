@@ -28,6 +28,8 @@ SIGNATURES = {
     "tsasr_joint_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "tsasr_joint_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _ll]),
     "tsasr_joint_bwd": (_i, [_vp] * 7 + [_i] * 7 + [_f] + [_vp] * 7 + [_sz, _ll] + [_vp] * 5),
+    "tsasr_prepare_lengths": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "tsasr_cast_operands_bf16": (_i, [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp]),
     "tsasr_joint_decode_workspace_bytes": (_sz, [_i]),
     "tsasr_joint_decode_step": (_i, [_vp, _vp, _ll, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _sz, _vp]),
     "tsasr_kernel_timing_enable": (_i, [_i]),

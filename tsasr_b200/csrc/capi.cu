@@ -29,6 +29,9 @@ cudaError_t launch_logits_grad(const void*, int, const int*, const int*, const i
                                float, void*, cudaStream_t);
 cudaError_t launch_logprobs_grad(const int*, const int*, const int*, int, int, int, int, int, const float2*,
                                  const float*, const float*, const float*, const float*, float*, cudaStream_t);
+// prep.cu
+cudaError_t launch_lengths(const float*, const float*, const int*, const int*, int, int, int, int*, int*, int*, cudaStream_t);
+cudaError_t launch_cast3(const float*, size_t, const float*, size_t, const float*, size_t, void*, void*, void*, int, cudaStream_t);
 // decode.cu
 cudaError_t launch_joint_decode_step(const float*, const float*, long long, long long, const float*, const float*, int, int, int,
                                      int, float, float*, void*, cudaStream_t);
@@ -391,6 +394,32 @@ int tsasr_joint_fwd(const void* enc, const void* dec, const void* W, const float
     if (int rc = make_joint_maps(&maps, p, enc, dec, W)) return rc;
     ScopedTiming tm("joint_gemm_kernel<FWD>", static_cast<cudaStream_t>(stream));
     return launch_joint<MODE_FWD>(maps, p, sms, static_cast<cudaStream_t>(stream));
+}
+
+int tsasr_prepare_lengths(const float* rel_logit_lengths, const float* rel_target_lengths, const int32_t* abs_logit_lengths,
+                          const int32_t* abs_target_lengths, int B, int T, int n_targets, int32_t* logit_lengths_out,
+                          int32_t* target_lengths_out, int32_t* stats_out, tsasr_stream_t stream) {
+    REQUIRE(B >= 1 && T >= 1 && n_targets >= 0, "B, T must be >= 1 and n_targets >= 0");
+    REQUIRE((rel_logit_lengths || abs_logit_lengths) && (rel_target_lengths || abs_target_lengths) && stats_out,
+            "null pointer argument");
+    cudaError_t e = launch_lengths(rel_logit_lengths, rel_target_lengths, abs_logit_lengths, abs_target_lengths, B, T, n_targets,
+                                   logit_lengths_out, target_lengths_out, stats_out, static_cast<cudaStream_t>(stream));
+    ++g_launches;
+    return e == cudaSuccess ? TSASR_OK : cuda_fail(e, "lengths_kernel");
+}
+
+int tsasr_cast_operands_bf16(const float* enc, size_t n_enc, const float* dec, size_t n_dec, const float* W, size_t n_w,
+                             void* enc16, void* dec16, void* W16, tsasr_stream_t stream) {
+    REQUIRE(enc && dec && W && enc16 && dec16 && W16, "null pointer argument");
+    REQUIRE(n_enc % 4 == 0 && n_dec % 4 == 0 && n_w % 4 == 0, "element counts must be multiples of 4");
+    REQUIRE(((reinterpret_cast<uintptr_t>(enc) | reinterpret_cast<uintptr_t>(dec) | reinterpret_cast<uintptr_t>(W)) & 15) == 0 &&
+                ((reinterpret_cast<uintptr_t>(enc16) | reinterpret_cast<uintptr_t>(dec16) | reinterpret_cast<uintptr_t>(W16)) & 7) == 0,
+            "operands must be 16-byte (fp32) / 8-byte (bf16) aligned");
+    int sms, max_smem;
+    if (int rc = device_info(&sms, &max_smem)) return rc;
+    cudaError_t e = launch_cast3(enc, n_enc, dec, n_dec, W, n_w, enc16, dec16, W16, sms, static_cast<cudaStream_t>(stream));
+    ++g_launches;
+    return e == cudaSuccess ? TSASR_OK : cuda_fail(e, "cast3_kernel");
 }
 
 size_t tsasr_joint_decode_workspace_bytes(int V) { return V >= 1 ? joint_decode_workspace_bytes(V) : 0; }

@@ -39,24 +39,23 @@ def _validate_lengths(logit_lengths, target_lengths, T, U, n_targets):
 
 
 class _DeferredLengthCheck:
-    """The same host-side checks, but read back on a side stream: the statistics are computed by tiny kernels
-    on the caller's stream BEFORE the fused kernels are queued and copied to pinned memory on a second stream,
-    so the host only waits for those tiny kernels while the GPU already works on the joint GEMM.  The fused
-    kernels clamp every length to the padded lattice, so an invalid input cannot index out of bounds before
-    ``finish`` raises (same exception types and messages as ``_validate_lengths``)."""
+    """The same host-side checks, read back on a side stream.  ``stats`` = int32 [max T_b, max labels, min T_b,
+    min labels] produced on the caller's stream by ONE small kernel (``tsasr_prepare_lengths``) before the fused
+    kernels are queued; ``ready`` is an event recorded right after it.  The copy to pinned memory runs on a second
+    stream, so ``finish`` -- called after the fused kernels have been queued -- only waits for that small kernel
+    while the GPU already works on the joint GEMM.  The fused kernels clamp every length to the padded lattice,
+    so an invalid input cannot index out of bounds before ``finish`` raises (same exception types and messages
+    as ``_validate_lengths``)."""
 
     _side, _pinned = {}, {}
 
-    def __init__(self, logit_lengths, target_lengths):
-        dev = logit_lengths.device
-        stats = torch.stack([logit_lengths.max(), target_lengths.max(), logit_lengths.min(), target_lengths.min()])
+    def __init__(self, stats, ready):
+        dev = stats.device
         side = self._side.get(dev)
         if side is None:
             side = self._side[dev] = torch.cuda.Stream(dev)
-            self._pinned[dev] = torch.empty((4,), dtype=stats.dtype).pin_memory()
+            self._pinned[dev] = torch.empty((4,), dtype=torch.int32).pin_memory()
         self.host = self._pinned[dev]
-        ready = torch.cuda.Event()
-        ready.record(torch.cuda.current_stream(dev))
         side.wait_event(ready)
         with torch.cuda.stream(side):
             self.host.copy_(stats, non_blocking=True)
@@ -75,6 +74,33 @@ class _DeferredLengthCheck:
             raise RuntimeError("target length mismatch")
         if min_t < 1 or min_l < 0:
             raise RuntimeError("logit_lengths must be >= 1 and target_lengths >= 0")
+
+
+def _prepare_lengths(logit_lengths, target_lengths, T, n_targets, relative):
+    """-> (int32 logit_lengths, int32 target_lengths, stats [4] int32, event recorded after the kernel).
+
+    relative=True: SpeechBrain relative lengths, converted exactly like SB/nnet/losses.py:58-59
+    (fp32 product, round-half-to-even, int32) inside the one kernel that also computes the statistics."""
+    dev = logit_lengths.device
+    B = logit_lengths.shape[0]
+    stats = torch.empty((4,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    stream = torch.cuda.current_stream(dev)
+    if relative:
+        rl = logit_lengths.to(torch.float32).contiguous()
+        rt = target_lengths.to(torch.float32).contiguous()
+        out = torch.empty((2, B), dtype=torch.int32, device=dev)
+        ll, tl = out[0], out[1]
+        _lib.check(lib.tsasr_prepare_lengths(rl.data_ptr(), rt.data_ptr(), None, None, B, int(T), int(n_targets),
+                                             ll.data_ptr(), tl.data_ptr(), stats.data_ptr(), stream.cuda_stream))
+    else:
+        ll = logit_lengths.to(torch.int32).contiguous()
+        tl = target_lengths.to(torch.int32).contiguous()
+        _lib.check(lib.tsasr_prepare_lengths(None, None, ll.data_ptr(), tl.data_ptr(), B, int(T), int(n_targets),
+                                             None, None, stats.data_ptr(), stream.cuda_stream))
+    ready = torch.cuda.Event()
+    ready.record(stream)
+    return ll, tl, stats, ready
 
 
 class RnntLossFromLogits(torch.autograd.Function):
@@ -171,6 +197,18 @@ class NumbaSemanticsTransducer(torch.autograd.Function):
         return ctx.grads.mul_(grad_output), None, None, None, None, None, None
 
 
+def _operands_bf16(enc, dec, W):
+    """bf16 copies of the three GEMM operands: one launch when all are contiguous fp32 (the recipe's case)."""
+    ts = (enc, dec, W)
+    if all(t.dtype == torch.float32 and t.is_contiguous() and t.numel() % 4 == 0 and t.data_ptr() % 16 == 0 for t in ts):
+        outs = tuple(torch.empty(t.shape, dtype=torch.bfloat16, device=t.device) for t in ts)
+        _lib.check(_lib.load().tsasr_cast_operands_bf16(
+            enc.data_ptr(), enc.numel(), dec.data_ptr(), dec.numel(), W.data_ptr(), W.numel(),
+            outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), torch.cuda.current_stream(enc.device).cuda_stream))
+        return outs
+    return tuple(t.to(torch.bfloat16).contiguous() for t in ts)
+
+
 class FusedJointRnnt(torch.autograd.Function):
     """costs[b] of joint("sum") + activation + head Linear + RNN-T loss without the 4-D tensors.
 
@@ -182,9 +220,7 @@ class FusedJointRnnt(torch.autograd.Function):
     @staticmethod
     def forward(ctx, enc, dec, W, bias, targets, logit_lengths, target_lengths, blank, act_kind, act_param,
                 max_chunk_cells):
-        enc16 = enc.detach().to(torch.bfloat16).contiguous()
-        dec16 = dec.detach().to(torch.bfloat16).contiguous()
-        W16 = W.detach().to(torch.bfloat16).contiguous()
+        enc16, dec16, W16 = _operands_bf16(enc.detach(), dec.detach(), W.detach())
         b32 = bias.detach().to(torch.float32).contiguous()
         B, T, _ = enc16.shape
         U = dec16.shape[1]
@@ -208,8 +244,9 @@ class FusedJointRnnt(torch.autograd.Function):
 
 def fused_joint_rnnt_loss(enc_out, dec_out, weight, bias, targets, logit_lengths, target_lengths, blank=0,
                           activation="leaky_relu", act_param=0.01, reduction="mean", check_lengths=True,
-                          max_chunk_cells=0):
-    """Functional form of the fused path (absolute int32 lengths)."""
+                          max_chunk_cells=0, relative_lengths=False):
+    """Functional form of the fused path.  Lengths are absolute int32 counts, or -- with ``relative_lengths=True`` --
+    SpeechBrain's relative floats, converted bit-exactly like SB/nnet/losses.py:58-59."""
     _check_reduction(reduction)
     if enc_out.dim() != 3 or dec_out.dim() != 3:
         raise ValueError("enc_out must be [B,T,H] and dec_out [B,U,H]")
@@ -218,6 +255,8 @@ def fused_joint_rnnt_loss(enc_out, dec_out, weight, bias, targets, logit_lengths
     V = weight.shape[0]
     if dec_out.shape[0] != B or dec_out.shape[2] != H or weight.shape[1] != H:
         raise ValueError("shape mismatch between enc_out, dec_out and weight")
+    if not (enc_out.is_cuda and logit_lengths.is_cuda and target_lengths.is_cuda):
+        raise ValueError("tsasr_b200 needs CUDA tensors; there is no CPU path")
     if bias is None:
         bias = torch.zeros((V,), dtype=torch.float32, device=enc_out.device)
     if blank < 0:
@@ -225,11 +264,12 @@ def fused_joint_rnnt_loss(enc_out, dec_out, weight, bias, targets, logit_lengths
     if not 0 <= blank < V:
         raise RuntimeError("blank must be within [0, logits.shape[-1])")
     targets = targets.to(torch.int32).contiguous()
-    logit_lengths = logit_lengths.to(torch.int32).contiguous()
-    target_lengths = target_lengths.to(torch.int32).contiguous()
-    check = _DeferredLengthCheck(logit_lengths, target_lengths) if check_lengths else None
-    costs = FusedJointRnnt.apply(enc_out, dec_out, weight, bias, targets, logit_lengths, target_lengths, int(blank),
-                                 _lib.ACT_CODES[activation], float(act_param), int(max_chunk_cells))
-    if check is not None:
-        check.finish(T, U, targets.shape[1])  # raises what torchaudio raises; the kernels above are already queued
+    with torch.cuda.device(enc_out.device):
+        logit_lengths, target_lengths, stats, ready = _prepare_lengths(logit_lengths, target_lengths, T, targets.shape[1],
+                                                                       relative_lengths)
+        costs = FusedJointRnnt.apply(enc_out, dec_out, weight, bias, targets, logit_lengths, target_lengths, int(blank),
+                                     _lib.ACT_CODES[activation], float(act_param), int(max_chunk_cells))
+        if check_lengths:
+            # raises what torchaudio raises; the kernels above are already queued
+            _DeferredLengthCheck(stats, ready).finish(T, U, targets.shape[1])
     return _reduce(costs, reduction)

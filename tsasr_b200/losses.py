@@ -35,19 +35,26 @@ def transducer_loss(logits, targets, input_lens, target_lens, blank_index, reduc
         True  -> torchaudio semantics (what the recipe runs): reduce_b(-log P_b), exact gradient.
         False -> the SpeechBrain Numba semantics: reduce_b(-log P_b / T_b), un-normalised gradient.
     """
+    if isinstance(logits, JointHandle) and logits.has_head and use_torchaudio:
+        enc = logits._enc.squeeze(2)   # [B,T,1,H] -> [B,T,H]
+        dec = logits._dec.squeeze(1)   # [B,1,U,H] -> [B,U,H]
+        code_to_name = {0: "leaky_relu", 1: "relu", 2: "tanh", 3: "identity"}
+        dev = enc.device
+        fp32_lens = input_lens.dtype == torch.float32 and target_lens.dtype == torch.float32
+        if not fp32_lens:  # unusual dtypes: the reference's own expression decides the rounding
+            input_lens = (input_lens * logits.shape[1]).round().int()
+            target_lens = (target_lens * targets.shape[1]).round().int()
+        # fp32 relative lengths: the conversion of losses.py:58-59 runs, bit-exact, inside tsasr_prepare_lengths
+        return F.fused_joint_rnnt_loss(
+            enc, dec, logits._weight, logits._bias, targets.to(dev), input_lens.to(dev), target_lens.to(dev),
+            blank=blank_index, activation=code_to_name[logits._act_code], act_param=logits._act_param,
+            reduction=reduction, relative_lengths=fp32_lens)
+
     # integer length conversion, bit-exact with losses.py:58-59 (fp32 multiply, round-half-even, int32)
     input_lens = (input_lens * logits.shape[1]).round().int()
     target_lens = (target_lens * targets.shape[1]).round().int()
 
     if isinstance(logits, JointHandle):
-        if logits.has_head and use_torchaudio:
-            enc = logits._enc.squeeze(2)   # [B,T,1,H] -> [B,T,H]
-            dec = logits._dec.squeeze(1)   # [B,1,U,H] -> [B,U,H]
-            code_to_name = {0: "leaky_relu", 1: "relu", 2: "tanh", 3: "identity"}
-            return F.fused_joint_rnnt_loss(
-                enc, dec, logits._weight, logits._bias, targets.to(input_lens.device), input_lens, target_lens,
-                blank=blank_index, activation=code_to_name[logits._act_code], act_param=logits._act_param,
-                reduction=reduction)
         logits = logits.materialize()
 
     if use_torchaudio:
