@@ -274,13 +274,13 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
             cfg.blockDim = dim3(kDjThreads);
             cfg.dynamicSmemBytes = djL.total;
             cfg.stream = st;
-            cudaLaunchAttribute attr[1];
+            cudaLaunchAttribute attr[2];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = dj_cs;
             attr[0].val.clusterDim.y = 1;
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
-            cfg.numAttrs = 1;
+            cfg.numAttrs = pdl_launch_attr(attr, 1);
             static const bool prof_on = getenv("TSASR_DEBUG_PROF") != nullptr;
             long long* d_prof = nullptr;
             BwdParams bpp = bp;
@@ -318,9 +318,9 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
             const int b0 = g0 / jp.nTt, b1 = (g1 - 1) / jp.nTt + 1;
             const int rows = (g1 - g0) * tT + (b1 - b0) * U;
             ScopedTiming tm("reduce_dpre_kernel", st);
-            reduce_dpre_kernel<<<rows, 160, 0, st>>>(bp, d_enc, d_dec);
+            e = launch_pdl(reduce_dpre_kernel, dim3(rows), dim3(160), 0, st, bp, d_enc, d_dec);
             ++g_launches;
-            if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "reduce_dpre_kernel launch");
+            if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "reduce_dpre_kernel launch");
         }
 
         bp.accumulate = chunk_idx > 0;
@@ -331,13 +331,13 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
             cfg.blockDim = dim3(kBwdThreads);
             cfg.dynamicSmemBytes = dwL.total;
             cfg.stream = st;
-            cudaLaunchAttribute attr[1];
+            cudaLaunchAttribute attr[2];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = 2;
             attr[0].val.clusterDim.y = 1;
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
-            cfg.numAttrs = 1;
+            cfg.numAttrs = pdl_launch_attr(attr, 1);
             static const bool prof_on = getenv("TSASR_DEBUG_PROF") != nullptr;
             long long* d_prof = nullptr;
             BwdParams bpp = bp;
@@ -374,10 +374,10 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
     (void)tU;
     {
         ScopedTiming tm("reduce_dw_kernel", st);
-        reduce_dw_kernel<<<sms * 2, 256, 0, st>>>(bp, dW, db);
+        e = launch_pdl(reduce_dw_kernel, dim3(sms * 2), dim3(256), 0, st, bp, dW, db);
     }
     ++g_launches;
-    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "reduce_dw_kernel launch");
+    if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "reduce_dw_kernel launch");
     return TSASR_OK;
 }
 

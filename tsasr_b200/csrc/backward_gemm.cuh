@@ -193,6 +193,7 @@ dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+    griddep_wait();  // the dY images are written by the preceding GRAD pass
 
     const int n_tiles = p.tile_end - p.tile_begin;
     const int n_pairs = (n_tiles + 1) >> 1;
@@ -322,6 +323,7 @@ dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 // chunks by read-modify-write (d_dec is zero-filled first).  Deterministic, no atomics.
 __global__ void __launch_bounds__(160)
 reduce_dpre_kernel(const BwdParams p, float* __restrict__ d_enc, float* __restrict__ d_dec) {
+    griddep_wait();
     const int tT = 1 << p.tT_log2, tU = kTileM >> p.tT_log2;
     const int g_begin = p.tile_begin / p.nTu, g_end = p.tile_end / p.nTu;
     const int n_enc_rows = (g_end - g_begin) * tT;
@@ -499,6 +501,7 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constan
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+    griddep_wait();
 
     if (warp_idx == kBwdWarpLoad) {
         uint32_t stage = 0, phase = 0;
@@ -642,6 +645,7 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constan
 }
 
 __global__ void reduce_dw_kernel(const BwdParams p, float* __restrict__ dW, float* __restrict__ db) {
+    griddep_wait();
     const size_t vrows = (size_t)p.NV2 * 256;
     const size_t n = (size_t)p.V * p.H;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {

@@ -245,13 +245,13 @@ static int launch_joint_impl(const JointMaps& maps, const JointParams& p, int nu
     cfg.blockDim = dim3(kNumThreads);
     cfg.dynamicSmemBytes = L.total;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? 2 : 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_launch_attr(attr, 1);
     e = cudaLaunchKernelEx(&cfg, kern, maps.w, pp);
     ++g_launches;
     if (e != cudaSuccess) return cuda_fail(e, "joint_gemm_kernel launch");

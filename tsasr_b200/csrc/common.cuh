@@ -9,6 +9,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+#include <cstring>
+
 namespace tsasr {
 
 // ------------------------------------------------------------------------------------------
@@ -46,6 +49,36 @@ __device__ __forceinline__ float logaddexp_fast(float a, float b) {
     const float m = fmaxf(a, b);
     if (m == -INFINITY) return -INFINITY;
     return m + __logf(1.f + __expf(-fabsf(a - b)));
+}
+
+// ------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start (set up barriers, allocate TMEM, prefetch descriptors) while its predecessor in the stream is still
+// draining; griddep_wait() blocks until the predecessor has completed and its writes are visible.  Every thread
+// calls it before the first access to data the predecessor produced.  Without the launch attribute it is a no-op.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// host side: appends the launch attribute (TSASR_DEBUG_NO_PDL=1 switches it off for A/B runs); returns the new count
+inline int pdl_launch_attr(cudaLaunchAttribute* attrs, int n) {
+    static const bool on = getenv("TSASR_DEBUG_NO_PDL") == nullptr;
+    if (!on) return n;
+    attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[n].val.programmaticStreamSerializationAllowed = 1;
+    return n + 1;
+}
+// <<<grid, block, smem, stream>>> with the attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_launch_attr(attr, 0);
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -317,6 +317,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
     else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);  // warp-uniform for the compiler
+    griddep_wait();  // everything above overlapped the previous kernel's tail (programmatic dependent launch)
 
     if (warp_idx == kWarpTmaW) {
         // ===================== W producer (TMA) =====================

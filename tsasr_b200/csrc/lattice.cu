@@ -298,6 +298,7 @@ alpha_beta_kernel(const float2* __restrict__ lat2, const int* __restrict__ logit
                   float* __restrict__ beta, float* __restrict__ ll_alpha, float* __restrict__ ll_beta) {
     __shared__ float xchg[64];
     extern __shared__ __align__(16) float2 dp_ring[];  // [kDpPrefetch][blockDim.x]
+    griddep_wait();  // lat2 comes from the preceding kernel (programmatic dependent launch)
     const int b = blockIdx.x;
     // lengths are clamped to the padded lattice: the fused path validates them on the host only after
     // launching (tsasr_b200/functional.py), so an invalid length must never index outside the slab
@@ -311,6 +312,7 @@ alpha_beta_kernel(const float2* __restrict__ lat2, const int* __restrict__ logit
 // cost[b] = -log P from the beta pass (torchaudio: costs = -beta(0,0)); written by a tiny kernel so the
 // DP kernel keeps both log-likelihoods available for the consistency check in tests.
 __global__ void finalize_cost_kernel(const float* __restrict__ ll_beta, float* __restrict__ cost, int B) {
+    griddep_wait();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) cost[b] = -ll_beta[b];
 }
@@ -490,11 +492,11 @@ cudaError_t launch_alpha_beta(const float2* lat2, const int* ll, const int* tl, 
         cudaFuncSetAttribute(alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDpPrefetch * 1024 * (int)sizeof(float2));
         attr_set = true;
     }
-    alpha_beta_kernel<<<dim3(B, 2), threads, ring_bytes, st>>>(lat2, ll, tl, Tmax, U, alpha, beta, ll_alpha, ll_beta);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    finalize_cost_kernel<<<(B + 127) / 128, 128, 0, st>>>(ll_beta, cost, B);
-    return cudaGetLastError();
+    cudaError_t e = launch_pdl(alpha_beta_kernel, dim3(B, 2), dim3(threads), ring_bytes, st, lat2, ll, tl, Tmax, U, alpha, beta,
+                               ll_alpha, ll_beta);
+    if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return e;
+    e = launch_pdl(finalize_cost_kernel, dim3((B + 127) / 128), dim3(128), 0, st, (const float*)ll_beta, cost, B);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 template <typename T>
