@@ -49,6 +49,8 @@ def main():
         ll = torch.randint(int(0.6 * T), T + 1, (B,), generator=g, dtype=torch.int32)
         tl = torch.randint(int(0.4 * U), U, (B,), generator=g, dtype=torch.int32)
         ll[0], tl[0] = T, U - 1
+    live = int(((ll.long() + 15) // 16 * 16 * ((tl.long() + 1 + 7) // 8 * 8)).sum()) if (T, U) == (400, 100) else None
+    print(f"lengths: T_b={ll.tolist()} labels={tl.tolist()}; cells in live 16x8 tiles: {live} of {B * T * U}")
     ll, tl = ll.to(dev), tl.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gemm = 2.0 * B * T * U * H * V

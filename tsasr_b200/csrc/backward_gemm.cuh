@@ -57,15 +57,6 @@ struct BwdParams {
     long long* prof;   // development: MMA-warp cycle counters per CTA (or nullptr)
 };
 
-__device__ __forceinline__ bool tile_live(const BwdParams& p, int tile) {
-    const int per_b = p.nTt * p.nTu;
-    const int b = tile / per_b;
-    const int rem = tile - b * per_b;
-    const int tt = rem / p.nTu, tu = rem - tt * p.nTu;
-    const int Tb = min(max(p.logit_lengths[b], 1), p.T), Ub = min(max(p.target_lengths[b], 0), p.U - 1) + 1;
-    return (tt << p.tT_log2) < Tb && tu * (kTileM >> p.tT_log2) < Ub;
-}
-
 // ------------------------------------------------------------------------------------------------
 // dJ GEMM (transposed) + activation backward + in-register broadcast-sum reductions
 // ------------------------------------------------------------------------------------------------
@@ -170,6 +161,7 @@ __global__ void __launch_bounds__(kDjThreads, 1)
 dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_dy, const BwdParams p) {
     constexpr int TT = 1 << TT_LOG2, TU = 128 >> TT_LOG2;
     extern __shared__ __align__(1024) uint8_t smem[];
+    griddep_wait();  // programmatic dependent launch: the dY images come from the preceding GRAD pass
     const DjSmem L = dj_smem_layout();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* full = bars;              // [kDjStages]  leader: bytes of BOTH CTAs' loads
@@ -193,27 +185,33 @@ dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
-    griddep_wait();  // the dY images are written by the preceding GRAD pass
-
-    const int n_tiles = p.tile_end - p.tile_begin;
-    const int n_pairs = (n_tiles + 1) >> 1;
-    const int n_units = n_pairs * p.NHC;  // consecutive units = the h-chunks of one tile pair (they share the dY images in L2)
-    auto live_local = [&](int tl) { return tl < n_tiles && tile_live(p, p.tile_begin + tl); };
+    // unit = (pair of consecutive LIVE tiles, h-chunk); consecutive units = the h-chunks of one tile pair (they share
+    // the dY images in L2).  tl0 / tl1: chunk-local ids of the pair's tiles (tl1 = -1: the last pair is incomplete).
+    const int n_live = count_live_tiles_warp(p);  // every warp counts for itself (converged here)
+    LiveCursor<BwdParams> cur(p, n_live);
+    auto open_unit = [&](int unit, int& c, int& tl0, int& tl1) -> bool {
+        const int pi = unit / p.NHC;
+        c = unit - pi * p.NHC;
+        if (!cur.seek(p, 2 * pi)) return false;
+        tl0 = cur.tile(p) - p.tile_begin;
+        tl1 = cur.seek(p, 2 * pi + 1) ? cur.tile(p) - p.tile_begin : -1;
+        return true;
+    };
 
     if (warp_idx == kDjWarpLoad) {
         // ===================== loads (whole warp, converged; one lane elected per instruction) =====================
         uint32_t stage = 0, phase = 0;
         const uint32_t full0 = mapa_u32(smem_u32(&full[0]), 0);  // the leader's barriers
-        for (int unit = cluster; unit < n_units; unit += n_clusters) {
-            const int pi = unit / p.NHC, c = unit - pi * p.NHC;
-            const bool live0 = live_local(2 * pi), live1 = live_local(2 * pi + 1);
-            if (!live0 && !live1) continue;
+        for (int unit = cluster;; unit += n_clusters) {
+            int c, tl0, tl1;
+            if (!open_unit(unit, c, tl0, tl1)) break;
             const int hbase = c * kDjChunkH;
             const int nbox0 = max(0, min(2, (p.H - hbase) >> 6)), nbox1 = max(0, min(2, (p.H - hbase - 128) >> 6));
-            const bool my_live = rank ? live1 : live0;
+            const int my_tl = rank ? tl1 : tl0;
+            const bool my_live = my_tl >= 0;
             const int my_nbox = rank ? nbox1 : nbox0, h0 = hbase + rank * 128;
-            const uint32_t bytes_pair = (uint32_t)(nbox0 + nbox1) * 8192u + (uint32_t)((int)live0 + (int)live1) * kImgBytes;
-            const int img_row0 = (2 * pi + rank) * p.NT4 * 128;
+            const uint32_t bytes_pair = (uint32_t)(nbox0 + nbox1) * 8192u + (uint32_t)(1 + (tl1 >= 0)) * kImgBytes;
+            const int img_row0 = my_tl * p.NT4 * 128;
             for (int kb = 0; kb < p.NVB; ++kb) {
                 mbar_wait(&empty[stage], phase ^ 1, 0x700 | stage);
                 __syncwarp();
@@ -233,9 +231,9 @@ dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem + L.stage_off) + 2 * 8192, 0, 1024);   // K-major
             long long t_acc = 0, t_full = 0, tm = 0;
             const long long t_begin = clock64();
+            // the issuing warp needs no tile coordinates, only the number of units: count the live tiles once
+            const int n_units = ((n_live + 1) >> 1) * p.NHC;
             for (int unit = cluster; unit < n_units; unit += n_clusters) {
-                const int pi = unit / p.NHC;
-                if (!live_local(2 * pi) && !live_local(2 * pi + 1)) continue;
                 const uint32_t buf = it & 1;
                 if (p.prof) tm = clock64();
                 mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 0x800 | buf);
@@ -266,14 +264,13 @@ dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         const uint32_t acc_empty0 = mapa_u32(smem_u32(&acc_empty[0]), 0);
         const int per_b = p.nTt * p.nTu;
         uint32_t it = 0;
-        for (int unit = cluster; unit < n_units; unit += n_clusters) {
-            const int pi = unit / p.NHC, c = unit - pi * p.NHC;
-            const bool live0 = live_local(2 * pi), live1 = live_local(2 * pi + 1);
-            if (!live0 && !live1) continue;
+        for (int unit = cluster;; unit += n_clusters) {
+            int c, tl0, tl1;
+            if (!open_unit(unit, c, tl0, tl1)) break;
             const uint32_t buf = it & 1;
-            const int tl = 2 * pi + g;
+            const int tl = g ? tl1 : tl0;
             const int h = c * kDjChunkH + rank * 128 + q * 32 + lane;
-            const bool work = (g ? live1 : live0) && (h - lane) < p.H;  // warp-uniform
+            const bool work = tl >= 0 && (h - lane) < p.H;  // warp-uniform
             float e[TT], d[TU];
             if (work) {
                 // the 24 pre-activation scalars of this thread's h (clamped rows: cells beyond T/U carry zero dY)
@@ -466,6 +463,7 @@ __device__ __forceinline__ int dw_slot_block(const BwdParams& p, const DwItem& i
 __global__ void __launch_bounds__(kBwdThreads, 1)
 dw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_j, const BwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    griddep_wait();  // programmatic dependent launch
     const DwSmem L = dw_smem_layout();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* full = bars;        // [kDwStages]  leader: bytes of both CTAs
@@ -476,8 +474,8 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constan
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
     const int pair = (int)cluster_id_x(), n_pairs = (int)num_clusters_x();
-    const int n_tiles = p.tile_end - p.tile_begin;
     const int n_items = p.hu_item0[p.NHU];
+    const int n_live = count_live_tiles_warp(p);  // every warp counts for itself (converged here)
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -501,8 +499,6 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constan
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
-    griddep_wait();
-
     if (warp_idx == kBwdWarpLoad) {
         uint32_t stage = 0, phase = 0;
         const uint32_t full0 = mapa_u32(smem_u32(&full[0]), 0);
@@ -512,8 +508,10 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constan
             for (int r = 0; r < 2; ++r)
                 for (int j = 0; j < 4; ++j) nB += dw_slot_block(p, it, r, j) >= 0;
             const uint32_t bytes_pair = (uint32_t)(4 + nB) * kDwHalfImg;
-            for (int tl = it.split; tl < n_tiles; tl += it.n_splits) {
-                if (!tile_live(p, p.tile_begin + tl)) continue;
+            LiveCursor<BwdParams> cur(p, n_live);
+            for (int k = it.split;; k += it.n_splits) {  // the item's share of the LIVE tiles
+                if (!cur.seek(p, k)) break;
+                const int tl = cur.tile(p) - p.tile_begin;
                 const int dy_row0 = (tl * p.NT4 + it.vt2 * 4 + rank * 2) * 128;
                 for (int half = 0; half < 2; ++half) {
                     mbar_wait(&empty[stage], phase ^ 1, 0xB00 | stage);
@@ -546,8 +544,7 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constan
                 const uint32_t idesc0 = make_idesc_bf16(256, it.nb0 * 64, 1, 1);
                 const uint32_t idesc1 = make_idesc_bf16(256, it.nb1 > 0 ? it.nb1 * 64 : 64, 1, 1);
                 bool first = true;
-                for (int tl = it.split; tl < n_tiles; tl += it.n_splits) {
-                    if (!tile_live(p, p.tile_begin + tl)) continue;
+                for (int k = it.split; k < n_live; k += it.n_splits) {  // the item's share of the live tiles
                     if (first) {  // the previous item's accumulator must have been drained by both CTAs
                         mbar_wait(acc_empty, (n_done & 1) ^ 1, 0xC80);
                         tcgen05_fence_after();
@@ -585,9 +582,8 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constan
         for (int item = pair; item < n_items; item += n_pairs) {
             const DwItem it = dw_item(p, item);
             const int v = it.vt2 * 256 + rank * 128 + row;
-            // did this split see any live tile?  (all roles agree; the epilogue must not wait otherwise)
-            bool any = false;
-            for (int tl = it.split; tl < n_tiles; tl += it.n_splits) any |= tile_live(p, p.tile_begin + tl);
+            // does this split own any live tile?  (all roles agree; the epilogue must not wait otherwise)
+            const bool any = it.split < n_live;
             float* wrow = p.dW_part + ((size_t)it.split * vrows + v) * p.H + it.hb0 * 64;
             if (any) {
                 mbar_wait(acc_full, n_done & 1, 0xD00);

@@ -23,6 +23,92 @@ __host__ __device__ __forceinline__ size_t skew_index(int b, int t, int u, int T
     return ((size_t)b * (size_t)(T + U - 1) + (size_t)(t + u)) * (size_t)U + (size_t)u;
 }
 
+// ------------------------------------------------------------------------------------------
+// Live cell tiles.  Tiles are numbered densely, tile = ((b * nTt + tt) * nTu + tu); those entirely outside the
+// utterance's T_b x U_b rectangle ("dead": ~40 % of a ragged batch) carry no data.  The kernels work on the k-th
+// LIVE tile, k = 0, 1, ...: per (b, tt) group either all ceil(U_b / tU) leading tiles are live or none, so a
+// cursor walking the groups finds the k-th live tile without any list in memory.  seek() is O(1) amortised for
+// non-decreasing k (it rewinds otherwise); every role of a kernel runs its own cursor and sees the same sequence.
+// P needs: logit_lengths, target_lengths, T, U, tT_log2, nTt, nTu, tile_begin, tile_end (whole groups).
+// ------------------------------------------------------------------------------------------
+template <typename P>
+struct LiveCursor {
+    // current group (b, tt) = dense group g; base = live tiles before it; after a successful seek tu is the tile's
+    // label-tile index inside the group.  dense = every tile of the range is live (full-length batch): the k-th live
+    // tile is simply tile_begin + k and the cursor degenerates to stateless index arithmetic.
+    int g, g_end, base, b, tt, tu, Tb, Ub, live_tt, n_u;
+    bool dense;
+    __device__ __forceinline__ void load_utterance(const P& p) {
+        // lengths are clamped to the padded lattice (validated on the host after launching)
+        const int tT = 1 << p.tT_log2, tU = 128 >> p.tT_log2;
+        Tb = min(max(p.logit_lengths[b], 1), p.T);
+        Ub = min(max(p.target_lengths[b], 0), p.U - 1) + 1;
+        live_tt = (Tb + tT - 1) >> p.tT_log2;
+        n_u = (Ub + tU - 1) / tU;
+    }
+    __device__ __forceinline__ void rewind(const P& p) {
+        g = p.tile_begin / p.nTu;
+        b = g / p.nTt;
+        tt = g - b * p.nTt;
+        base = 0;
+        if (g < g_end) load_utterance(p);
+    }
+    // n_live: count_live_tiles_warp(p) of the same range (every role computes it once, as a converged warp)
+    __device__ __forceinline__ LiveCursor(const P& p, int n_live)
+        : g_end(p.tile_end / p.nTu), tu(0), dense(n_live == p.tile_end - p.tile_begin) {
+        if (dense) { g = 0; base = 0; b = -1; tt = 0; Tb = 0; Ub = 0; live_tt = 0; n_u = 0; }
+        else rewind(p);
+    }
+    // positions the cursor on the k-th live tile of [tile_begin, tile_end); false when there are fewer
+    __device__ __forceinline__ bool seek(const P& p, int k) {
+        if (dense) {
+            const int tile = p.tile_begin + k;
+            if (tile >= p.tile_end) return false;
+            g = tile / p.nTu;
+            tu = tile - g * p.nTu;
+            const int bb = g / p.nTt;
+            tt = g - bb * p.nTt;
+            if (bb != b) { b = bb; load_utterance(p); }
+            return true;
+        }
+        if (k < base) rewind(p);
+        for (;;) {
+            if (g >= g_end) return false;
+            const int n = tt < live_tt ? n_u : 0;
+            if (k < base + n) { tu = k - base; return true; }
+            base += n;
+            ++g;
+            if (++tt == p.nTt) {
+                tt = 0;
+                ++b;
+                if (g < g_end) load_utterance(p);
+            }
+        }
+    }
+    __device__ __forceinline__ int tile(const P& p) const { return g * p.nTu + tu; }  // dense tile id
+};
+
+// Number of live tiles of [tile_begin, tile_end), computed cooperatively by one converged warp (lane l takes
+// utterances l, l+32, ...).  Roles that only need to know HOW MANY rounds there are (MMA issue, W stream, relays)
+// use this once instead of walking a cursor on their critical path.
+template <typename P>
+__device__ __forceinline__ int count_live_tiles_warp(const P& p) {
+    const int lane = threadIdx.x & 31;
+    const int g0 = p.tile_begin / p.nTu, g1 = p.tile_end / p.nTu;
+    const int b0 = g0 / p.nTt, b1 = (g1 + p.nTt - 1) / p.nTt;
+    const int tT = 1 << p.tT_log2, tU = 128 >> p.tT_log2;
+    int n = 0;
+    for (int b = b0 + lane; b < b1; b += 32) {
+        const int Tb = min(max(p.logit_lengths[b], 1), p.T), Ub = min(max(p.target_lengths[b], 0), p.U - 1) + 1;
+        const int live_tt = (Tb + tT - 1) >> p.tT_log2, n_u = (Ub + tU - 1) / tU;
+        const int lo = max(0, g0 - b * p.nTt), hi = min(min(p.nTt, g1 - b * p.nTt), live_tt);
+        n += max(0, hi - lo) * n_u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    return n;
+}
+
 enum ActKind : int { ACT_LEAKY_RELU = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_IDENTITY = 3 };
 
 __device__ __forceinline__ float act_apply(float x, int kind, float param) {

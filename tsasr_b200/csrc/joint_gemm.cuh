@@ -108,44 +108,45 @@ struct JointParams {
 
 struct TileCoord { int b, t0, u0, Tb, Ub; bool live; };
 
-__device__ __forceinline__ TileCoord tile_coord(const JointParams& p, int tile) {
-    TileCoord c;
-    if (tile >= p.tile_end) {  // the odd tile of the last pair
-        c.b = 0; c.t0 = 0; c.u0 = 0; c.Tb = 0; c.Ub = 0; c.live = false;
-        return c;
-    }
-    const int per_b = p.nTt * p.nTu;
-    c.b = tile / per_b;
-    const int rem = tile - c.b * per_b;
-    const int tt = rem / p.nTu;
-    const int tu = rem - tt * p.nTu;
-    const int tT = 1 << p.tT_log2, tU = kTileM >> p.tT_log2;
-    c.t0 = tt * tT;
-    c.u0 = tu * tU;
-    c.Tb = min(max(p.logit_lengths[c.b], 1), p.T);          // clamped: validated on the host after launching
-    c.Ub = min(max(p.target_lengths[c.b], 0), p.U - 1) + 1;
-    c.live = c.t0 < c.Tb && c.u0 < c.Ub;
-    return c;
-}
-
-// Work distribution.  Single CTA: CTA c takes tiles c, c+G, ...  Pair: cluster c takes tile pairs
-// (2c, 2c+1), (2c+2C, ...), rank r of the pair works on tile 2c+r.  A round is skipped by every role of
-// both CTAs when no tile of it is live; a CTA whose own tile is dead while its partner's is live still runs
-// the barrier protocol ("dummy" round) because the pair's MMA stream is shared.
+// Work distribution over the LIVE tiles (common.cuh, LiveCursor).  Single CTA: CTA c takes live tiles c, c+G, ...
+// Pair: cluster c takes live-tile pairs (2c, 2c+1), (2c+2C, ...), rank r works on the pair's r-th tile.  Only the
+// very last pair can be incomplete: the CTA without a tile still runs the barrier protocol ("dummy" round)
+// because the pair's MMA stream is shared.
 template <bool PAIR>
 struct Rounds {
-    int first, step, rank;
-    __device__ __forceinline__ Rounds(const JointParams& p) {
+    int next_round, step, rank;
+    LiveCursor<JointParams> cur;
+    // n_live = count_live_tiles_warp(p), computed by the calling (converged) warp
+    __device__ __forceinline__ Rounds(const JointParams& p, int n_live) : cur(p, n_live) {
         rank = PAIR ? (int)cluster_ctarank() : 0;
-        first = p.tile_begin + (PAIR ? 2 * (int)cluster_id_x() : (int)blockIdx.x);
-        step = PAIR ? 2 * (int)num_clusters_x() : (int)gridDim.x;
+        next_round = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;
+        step = PAIR ? (int)num_clusters_x() : (int)gridDim.x;
     }
-    // returns false when the round is dead for the whole unit; tc describes this CTA's own tile
-    __device__ __forceinline__ bool open(const JointParams& p, int t0, int& my_tile, TileCoord& tc) const {
-        my_tile = t0 + rank;
-        tc = tile_coord(p, my_tile);
-        if (!PAIR) return tc.live;
-        return tc.live || tile_coord(p, t0 + (rank ^ 1)).live;
+    // rounds of this unit when the number of live tiles is known (roles that need no tile coordinates)
+    __device__ __forceinline__ int count_my_rounds(int n_live) const {
+        const int total = PAIR ? (n_live + 1) >> 1 : n_live;
+        return next_round < total ? (total - next_round + step - 1) / step : 0;
+    }
+    // advances to this unit's next round; false when the live tiles are exhausted.  tc describes this CTA's own tile
+    // (tc.live = false, my_tile = -1: the missing partner tile of the last, odd pair).
+    __device__ __forceinline__ bool next(const JointParams& p, int& my_tile, TileCoord& tc) {
+        const int k0 = PAIR ? 2 * next_round : next_round;
+        next_round += step;
+        if (!cur.seek(p, k0)) return false;
+        tc.live = true;
+        if (PAIR && rank) tc.live = cur.seek(p, k0 + 1);
+        if (tc.live) {
+            my_tile = cur.tile(p);
+            tc.b = cur.b;
+            tc.t0 = cur.tt << p.tT_log2;
+            tc.u0 = cur.tu * (kTileM >> p.tT_log2);
+            tc.Tb = cur.Tb;
+            tc.Ub = cur.Ub;
+        } else {
+            my_tile = -1;
+            tc.b = 0; tc.t0 = 0; tc.u0 = 0; tc.Tb = 0; tc.Ub = 0;
+        }
+        return true;
     }
 };
 
@@ -182,7 +183,7 @@ __device__ __forceinline__ float act_t(float x, float param) {
 template <int MODE, int ACT, bool PAIR>
 __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a, const __nv_bfloat16* __restrict__ enc,
                                           const __nv_bfloat16* __restrict__ dec, uint64_t* a_full, uint64_t* a_empty) {
-    const Rounds<PAIR> rounds(p);
+    Rounds<PAIR> rounds(p, count_live_tiles_warp(p));
     // The partner CTA's producers arrive on a LOCAL barrier (a_full points at a_done there); a relay warp
     // forwards it to the leader.  A remote arrive has cluster-scope release semantics (MEMBAR.GPU), which in
     // MODE_GRAD would make every producer warp wait for its J-image global stores to drain.
@@ -201,10 +202,10 @@ __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a,
         ti[i] = r & tTm;
         ui[i] = r >> p.tT_log2;
     }
-    for (int t0 = rounds.first; t0 < p.tile_end; t0 += rounds.step) {
+    for (;;) {
         int tile;
         TileCoord tc;
-        if (!rounds.open(p, t0, tile, tc)) continue;
+        if (!rounds.next(p, tile, tc)) break;
         if (!tc.live || (p.dbg_skip & 2)) {  // dummy round: keep the pair's barrier protocol going, produce nothing
             for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(&a_empty[kb], (it & 1) ^ 1, 0x540 | kb);
@@ -275,6 +276,7 @@ template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(kNumThreads, 1)
 joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    griddep_wait();  // programmatic dependent launch: nothing below may read global memory before the predecessor is done
     const SmemLayout L = smem_layout(p.KB, p.num_w_stages);
     uint8_t* smem_a = smem + L.a_off;
     uint8_t* smem_w = smem + L.w_off;
@@ -294,7 +296,8 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int KB = p.KB, NT = p.NT, NS = p.num_w_stages;
-    const Rounds<PAIR> rounds(p);
+    const int n_live = count_live_tiles_warp(p);  // every warp counts for itself (a few hundred cycles, once)
+    Rounds<PAIR> rounds(p, n_live);  // per-thread cursor over the live tiles; every role walks the same sequence
     const bool leader = rounds.rank == 0;
     constexpr uint32_t kCtas = PAIR ? 2 : 1;
 
@@ -317,18 +320,14 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
     else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);  // warp-uniform for the compiler
-    griddep_wait();  // everything above overlapped the previous kernel's tail (programmatic dependent launch)
-
     if (warp_idx == kWarpTmaW) {
         // ===================== W producer (TMA) =====================
         // PAIR: the leader fills BOTH halves of a stage (its own and, by multicast to CTA 1, its partner's),
         // so the refill latency is commit -> leader wake-up -> TMA, with no detour through the partner.
         if (leader && !(p.dbg_skip & 4)) {  // whole warp, converged; one lane is elected inside each issuing instruction
             uint32_t stage = 0, phase = 0;
-            for (int t0 = rounds.first; t0 < p.tile_end; t0 += rounds.step) {
-                int tile;
-                TileCoord tc;
-                if (!rounds.open(p, t0, tile, tc)) continue;
+            const int my_rounds = rounds.count_my_rounds(n_live);
+            for (int round = 0; round < my_rounds; ++round) {
                 for (int nt = 0; nt < NT; ++nt) {
                     const int vt = nt;
                     if (PAIR) {
@@ -375,10 +374,8 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
             const uint32_t a_lo0 = (uint32_t)a_desc0, w_lo0 = (uint32_t)w_desc0;
             long long t_acc = 0, t_a = 0, t_w = 0, tm = 0, t_commit[3] = {0, 0, 0}, l_sum = 0, l_cnt = 0;
             const long long t_begin = clock64();
-            for (int t0 = rounds.first; t0 < p.tile_end; t0 += rounds.step) {
-                int tile;
-                TileCoord tc;
-                if (!rounds.open(p, t0, tile, tc)) continue;
+            const int my_rounds = rounds.count_my_rounds(n_live);
+            for (int round = 0; round < my_rounds; ++round) {
                 for (int nt = 0; nt < NT; ++nt, ++acc_it) {
                     const uint32_t buf = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
                     if (p.prof) tm = clock64();
@@ -440,10 +437,8 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
             // partner CTA: relay "all 8 epilogue warps released accumulator buffer b" to the leader's acc_empty
             const uint32_t acc_empty_leader = mapa_u32(smem_u32(&acc_empty[0]), 0);
             uint32_t acc_it = 0;
-            for (int t0 = rounds.first; t0 < p.tile_end; t0 += rounds.step) {
-                int tile;
-                TileCoord tc;
-                if (!rounds.open(p, t0, tile, tc)) continue;
+            const int my_rounds = rounds.count_my_rounds(n_live);
+            for (int round = 0; round < my_rounds; ++round) {
                 for (int nt = 0; nt < NT; ++nt, ++acc_it) {
                     const uint32_t buf = acc_it & 1;
                     mbar_wait(&acc_done[buf], (acc_it >> 1) & 1, 0x280 | buf);
@@ -457,10 +452,8 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
         if (!leader) {
             const uint32_t a_full_leader = mapa_u32(smem_u32(&a_full[0]), 0);
             uint32_t it = 0;
-            for (int t0 = rounds.first; t0 < p.tile_end; t0 += rounds.step) {
-                int tile;
-                TileCoord tc;
-                if (!rounds.open(p, t0, tile, tc)) continue;
+            const int my_rounds = rounds.count_my_rounds(n_live);
+            for (int round = 0; round < my_rounds; ++round) {
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&a_done[kb], it & 1, 0x380 | kb);
                     __syncwarp();
@@ -494,10 +487,10 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
         int nb_nt = -1;
         // the partner CTA releases accumulators on a local barrier that its relay warp forwards to the leader
         uint64_t* acc_release = (PAIR && !leader) ? acc_done : acc_empty;
-        for (int t0 = rounds.first; t0 < p.tile_end; t0 += rounds.step) {
+        for (;;) {
             int tile;
             TileCoord tc;
-            if (!rounds.open(p, t0, tile, tc)) continue;
+            if (!rounds.next(p, tile, tc)) break;
             if (!tc.live || (p.dbg_skip & 1)) {  // dummy round: release the accumulators the pair's MMA stream wrote for us
                 for (int nt = 0; nt < NT; ++nt, ++acc_it) {
                     const uint32_t buf = acc_it & 1;
