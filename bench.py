@@ -33,8 +33,9 @@ METRIC = "lattice cells/sec (B*T*U) joint+RNN-T fwd+bwd"
 UNIT = "cells/s"
 
 
-def synth(cfg, device, seed=0):
-    """Synthetic inputs of SURVEY.md section 8d: enc/dec ~ 0.5*randn, W/b ~ nn.Linear init, full lengths."""
+def synth(cfg, device, seed=0, ragged=False):
+    """Synthetic inputs of SURVEY.md section 8d: enc/dec ~ 0.5*randn, W/b ~ nn.Linear init; full lengths, or
+    (ragged) T_b in [0.6 T, T] and label counts in [0.4 U, U-1] with one utterance at the maximum of each."""
     g = torch.Generator().manual_seed(seed)
     B, T, U, V, H = (cfg[k] for k in "BTUVH")
     enc = 0.5 * torch.randn(B, T, H, generator=g)
@@ -45,6 +46,10 @@ def synth(cfg, device, seed=0):
     targets = torch.randint(1, V, (B, U - 1), generator=g, dtype=torch.int32)
     ll = torch.full((B,), T, dtype=torch.int32)
     tl = torch.full((B,), U - 1, dtype=torch.int32)
+    if ragged:
+        ll = torch.randint(int(0.6 * T), T + 1, (B,), generator=g, dtype=torch.int32)
+        tl = torch.randint(int(0.4 * U), U, (B,), generator=g, dtype=torch.int32)
+        ll[0], tl[0] = T, U - 1
     return [x.to(device) for x in (enc, dec, W, b, targets, ll, tl)]
 
 
@@ -229,6 +234,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ragged", action="store_true",
+                    help="ragged utterance lengths (SURVEY 8d) instead of the full-length batch the headline is quoted on")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -260,7 +267,7 @@ def main():
     cfg = CFG
     B, T, U, V, H = (cfg[k] for k in "BTUVH")
     cells = B * T * U
-    enc, dec, Wt, bias, targets, ll, tl = synth(cfg, dev, seed=rank)
+    enc, dec, Wt, bias, targets, ll, tl = synth(cfg, dev, seed=rank, ragged=args.ragged)
     enc16, dec16, W16 = enc.bfloat16().contiguous(), dec.bfloat16().contiguous(), Wt.bfloat16().contiguous()
     dcost = torch.full((B,), 1.0 / (B * world), dtype=torch.float32, device=dev)
     act = _lib.ACT_CODES[cfg["act"]]
@@ -332,7 +339,8 @@ def main():
         head.bias.copy_(bias)
     h_enc, h_dec = enc.cpu().pin_memory(), dec.cpu().pin_memory()
     h_tg = targets.cpu().long().pin_memory()
-    h_il, h_tl = torch.ones(B).pin_memory(), torch.ones(B).pin_memory()  # relative lengths (SpeechBrain convention)
+    # relative lengths (SpeechBrain convention)
+    h_il, h_tl = (ll.cpu().float() / T).pin_memory(), (tl.cpu().float() / (U - 1)).pin_memory()
     h2d = sum(x.numel() * x.element_size() for x in (h_enc, h_dec, h_tg, h_il, h_tl))
 
     copy_stream = torch.cuda.Stream(dev)
@@ -415,7 +423,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(), "B_per_gpu": B, "T": T, "U": U, "V": V, "H": H,
-                       "lengths": "full", "activation": cfg["act"], "parallelism": f"utterance-sharded dp{world}",
+                       "lengths": "ragged (T_b in [0.6T,T], labels in [0.4U,U-1])" if args.ragged else "full", "activation": cfg["act"], "parallelism": f"utterance-sharded dp{world}",
                        "l2": "flushed between timed steps with a 256 MiB write (untimed); step timed with CUDA events"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "api": "Transducer_joint -> nn.Linear head -> transducer_loss(handle) -> backward, fp32 pinned host inputs; "
