@@ -263,3 +263,22 @@ def test_relative_length_conversion_kernel_is_bit_exact():
         assert stats.cpu().tolist() == [int(want_l.max()), int(want_t.max()), int(want_l.min()), int(want_t.min())]
         ll2, tl2, stats2, _ = _prepare_lengths(want_l.to(d), want_t.to(d), T, n_tg, relative=False)
         assert torch.equal(ll2.cpu(), want_l) and stats2.cpu().tolist() == stats.cpu().tolist()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_half_precision_operands_need_no_cast_and_return_their_dtype(dtype):
+    """SURVEY 8f N1 (projections as producers): when encoder_proj / decoder_proj already emit bf16 (autocast), enc_out and
+    dec_out enter the fused op as they are and their gradients come back in the same dtype."""
+    B, T, U, H, V = 2, 24, 9, 64, 40
+    enc, dec, W, b, targets, ll, tl = _inputs(B, T, U, H, V, seed=3)
+    d = _dev()
+    e, dc = (x.to(d).to(dtype).requires_grad_() for x in (enc, dec))
+    w, bb = W.to(d).float().requires_grad_(), b.to(d).requires_grad_()
+    costs = tsasr_b200.fused_joint_rnnt_loss(e, dc, w, bb, targets.to(d), ll.to(d), tl.to(d), blank=0, reduction="none")
+    costs.sum().backward()
+    assert e.grad.dtype == dtype and dc.grad.dtype == dtype and w.grad.dtype == torch.float32
+    ref = reference_joint_loss_fwd_bwd(e.detach().float().cpu(), dc.detach().float().cpu(), W, b, targets, ll, tl, 0, "leaky_relu",
+                                       0.01, round_bf16=True)
+    tol = LOSS_RTOL if dtype == torch.bfloat16 else 2e-3  # fp16 inputs are re-rounded to bf16 operands
+    np.testing.assert_allclose(costs.detach().cpu().numpy(), ref["costs"].numpy(), rtol=tol)
+    assert _rel_err(e.grad.float().cpu(), ref["d_enc"]) < 2e-2 and _rel_err(w.grad.cpu(), ref["dW"]) < 2e-2
