@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TSASR_ABI_VERSION 1
+#define TSASR_ABI_VERSION 2
 
 enum {
     TSASR_OK = 0,
@@ -104,13 +104,19 @@ size_t tsasr_joint_bwd_workspace_bytes(int B, int T, int U, int H, int V, long l
 /* Backward of the fused chain (autograd of Linear + activation + broadcast add fed by the loss
  * gradient; reference: SB/core.py:1077 loss.backward()).  Recomputes the logits tile-wise, forms
  * dlogits in bf16 chunk by chunk (never the whole [B,T,U,V]) and runs the two backward GEMMs.
- *   out: d_enc fp32 [B,T,H], d_dec fp32 [B,U,H], dW fp32 [V,H], db fp32 [V]  (all overwritten). */
+ *   out: d_enc fp32 [B,T,H], d_dec fp32 [B,U,H], dW fp32 [V,H], db fp32 [V]  (all overwritten).
+ * prune_log2_eps < 0: 128-cell tiles whose largest alignment posterior exp(alpha + beta - L) is below
+ * 2^prune_log2_eps are left out of the backward (every term of their dlogits carries that factor; at -30 what is
+ * dropped is below fp32 resolution next to the O(1) terms of the alignment band).  >= 0: every live tile is processed.
+ * tsasr_joint_bwd_stats_offset(): byte offset, from the workspace base rounded up to 1024, of three int32
+ * {active tiles of the last chunk, active tiles, live tiles} written by the call (measurement aid). */
+size_t tsasr_joint_bwd_stats_offset(int B, int T, int U, int H, int V, long long max_chunk_cells);
 int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float* bias, const int32_t* targets,
                     const int32_t* logit_lengths, const int32_t* target_lengths, int B, int T, int U, int H, int V,
                     int blank, int act_kind, float act_param, const float* lat2, const float* logz,
                     const float* alpha, const float* beta, const float* cost, const float* dcost, void* workspace,
-                    size_t workspace_bytes, long long max_chunk_cells, float* d_enc, float* d_dec, float* dW,
-                    float* db, tsasr_stream_t stream);
+                    size_t workspace_bytes, long long max_chunk_cells, float prune_log2_eps, float* d_enc, float* d_dec,
+                    float* dW, float* db, tsasr_stream_t stream);
 
 /* ---- host-path helpers of the fused loss (one launch each instead of a dozen elementwise launches) -------
  * tsasr_prepare_lengths: the integer length conversion of SB/nnet/losses.py:58-59, bit-exact

@@ -161,7 +161,7 @@ def test_fused_dlogits_images_vs_oracle():
     d = _dev()
     e, dc, w, bb = (x.to(d).float().requires_grad_() for x in (enc, dec, W, b))
     costs = tsasr_b200.fused_joint_rnnt_loss(e, dc, w, bb, targets.to(d), ll.to(d), tl.to(d), blank=0,
-                                             reduction="none", max_chunk_cells=1 << 30)
+                                             reduction="none", max_chunk_cells=1 << 30, prune_log2_eps=0.0)  # every tile written
     costs.sum().backward()
     torch.cuda.synchronize()
     got = _decode_dy_images(ops._workspaces[d], B, T, U, V).numpy()
@@ -282,3 +282,24 @@ def test_half_precision_operands_need_no_cast_and_return_their_dtype(dtype):
     tol = LOSS_RTOL if dtype == torch.bfloat16 else 2e-3  # fp16 inputs are re-rounded to bf16 operands
     np.testing.assert_allclose(costs.detach().cpu().numpy(), ref["costs"].numpy(), rtol=tol)
     assert _rel_err(e.grad.float().cpu(), ref["d_enc"]) < 2e-2 and _rel_err(w.grad.cpu(), ref["dW"]) < 2e-2
+
+
+def test_backward_tile_pruning_is_invisible_in_fp32():
+    """Tiles whose alignment posterior stays below 2^-30 are skipped by the backward: the gradients must agree with the
+    unpruned run to fp32 rounding, while a substantial share of the tiles is actually skipped."""
+    B, T, U, H, V = 3, 300, 80, 128, 500
+    enc, dec, W, b, targets, ll, tl = _inputs(B, T, U, H, V, seed=9)
+    d = _dev()
+    outs = []
+    for eps in (0.0, -30.0):
+        e, dc, w, bb = (x.to(d).float().requires_grad_() for x in (enc, dec, W, b))
+        costs = tsasr_b200.fused_joint_rnnt_loss(e, dc, w, bb, targets.to(d), ll.to(d), tl.to(d), blank=0, reduction="none",
+                                                 prune_log2_eps=eps)
+        costs.sum().backward()
+        torch.cuda.synchronize()
+        outs.append(([g.grad.clone() for g in (e, dc, w, bb)], ops.last_backward_tile_stats(d)))
+    (dense, st0), (pruned, st1) = outs
+    assert st0 == (0, 0)                                   # switched off: no activity pass at all
+    assert 0 < st1[0] < 0.85 * st1[1], st1                 # the far corners of the lattice are skipped
+    for a, c in zip(dense, pruned):
+        assert _rel_err(c, a) < 1e-5

@@ -27,7 +27,8 @@ SIGNATURES = {
     "tsasr_logprobs_grad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsasr_joint_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "tsasr_joint_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _ll]),
-    "tsasr_joint_bwd": (_i, [_vp] * 7 + [_i] * 7 + [_f] + [_vp] * 7 + [_sz, _ll] + [_vp] * 5),
+    "tsasr_joint_bwd_stats_offset": (_sz, [_i, _i, _i, _i, _i, _ll]),
+    "tsasr_joint_bwd": (_i, [_vp] * 7 + [_i] * 7 + [_f] + [_vp] * 7 + [_sz, _ll, _f] + [_vp] * 5),
     "tsasr_prepare_lengths": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "tsasr_cast_operands_bf16": (_i, [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp]),
     "tsasr_joint_decode_workspace_bytes": (_sz, [_i]),
@@ -58,7 +59,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.tsasr_abi_version() != 1:
+    if lib.tsasr_abi_version() != 2:
         raise RuntimeError("libtsasr_b200.so ABI version mismatch")
     _lib = lib
     return lib

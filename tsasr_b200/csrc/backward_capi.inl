@@ -16,7 +16,7 @@ struct BwdPlan {
     int n_chunks;
     int NV2, NHU, NVB, NT4;
     int hu_blk[3], hu_splits[3], hu_item0[3], max_splits, dw_pairs;
-    size_t dY_bytes, J_bytes, part_bytes, dW_bytes, db_bytes, total;
+    size_t dY_bytes, J_bytes, part_bytes, dW_bytes, db_bytes, prune_bytes, total;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -138,7 +138,9 @@ static void plan_bwd(const JointParams& jp, int num_sms, long long max_chunk_cel
     pl->part_bytes = align_up((size_t)pl->chunk_tiles * (tT + tU) * jp.H * 4, 1024);
     pl->dW_bytes = align_up((size_t)pl->max_splits * pl->NV2 * 256 * jp.H * 4, 1024);
     pl->db_bytes = align_up((size_t)pl->max_splits * pl->NV2 * 256 * 4, 1024);
-    pl->total = pl->dY_bytes + pl->J_bytes + pl->part_bytes + pl->dW_bytes + pl->db_bytes + 1024;
+    // tile pruning: stats (64 B) | flags (1 B per chunk tile) | ids (4 B per chunk tile)
+    pl->prune_bytes = align_up(64 + align_up((size_t)pl->chunk_tiles, 16) + 4 * (size_t)pl->chunk_tiles, 1024);
+    pl->total = pl->dY_bytes + pl->J_bytes + pl->part_bytes + pl->dW_bytes + pl->db_bytes + pl->prune_bytes + 1024;
 }
 
 static int fake_params_for_plan(JointParams& p, int B, int T, int U, int H, int V) {
@@ -168,12 +170,22 @@ size_t tsasr_joint_bwd_workspace_bytes(int B, int T, int U, int H, int V, long l
     return pl.total;
 }
 
+size_t tsasr_joint_bwd_stats_offset(int B, int T, int U, int H, int V, long long max_chunk_cells) {
+    JointParams p;
+    if (fake_params_for_plan(p, B, T, U, H, V) != 0) return 0;
+    int sms = 148, max_smem = 0;
+    if (device_info(&sms, &max_smem) != TSASR_OK) sms = 148;
+    BwdPlan pl;
+    plan_bwd(p, sms, max_chunk_cells, &pl);
+    return pl.dY_bytes + pl.J_bytes + pl.part_bytes + pl.dW_bytes + pl.db_bytes;  // relative to the 1024-aligned workspace base
+}
+
 int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float* bias, const int32_t* targets,
                     const int32_t* logit_lengths, const int32_t* target_lengths, int B, int T, int U, int H, int V,
                     int blank, int act_kind, float act_param, const float* lat2, const float* logz,
                     const float* alpha, const float* beta, const float* cost, const float* dcost, void* workspace,
-                    size_t workspace_bytes, long long max_chunk_cells, float* d_enc, float* d_dec, float* dW,
-                    float* db, tsasr_stream_t stream) {
+                    size_t workspace_bytes, long long max_chunk_cells, float prune_log2_eps, float* d_enc, float* d_dec,
+                    float* dW, float* db, tsasr_stream_t stream) {
     if (int rc = check_dims(B, T, U, V, blank)) return rc;
     REQUIRE(enc && dec && W && bias && logit_lengths && target_lengths && lat2 && logz && alpha && beta && cost &&
                 workspace && d_enc && d_dec && dW && db, "null pointer argument");
@@ -215,6 +227,11 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
     bp.dpre_part = reinterpret_cast<float*>(ws + pl.dY_bytes + pl.J_bytes);
     bp.dW_part = reinterpret_cast<float*>(ws + pl.dY_bytes + pl.J_bytes + pl.part_bytes);
     bp.db_part = reinterpret_cast<float*>(ws + pl.dY_bytes + pl.J_bytes + pl.part_bytes + pl.dW_bytes);
+    uint8_t* prune_base = ws + pl.dY_bytes + pl.J_bytes + pl.part_bytes + pl.dW_bytes + pl.db_bytes;
+    int* prune_stats = reinterpret_cast<int*>(prune_base);
+    uint8_t* prune_flags = prune_base + 64;
+    int* prune_ids = reinterpret_cast<int*>(prune_base + 64 + align_up((size_t)pl.chunk_tiles, 16));
+    const bool prune = prune_log2_eps < 0.f;
     bp.NV2 = pl.NV2; bp.NHU = pl.NHU;
     for (int i = 0; i < 3; ++i) { bp.hu_blk[i] = pl.hu_blk[i]; bp.hu_item0[i] = pl.hu_item0[i]; }
     bp.hu_splits[0] = pl.hu_splits[0]; bp.hu_splits[1] = pl.hu_splits[1];
@@ -232,6 +249,8 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(d_enc)");
     e = cudaMemsetAsync(d_dec, 0, sizeof(float) * (size_t)B * U * H, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(d_dec)");
+    e = cudaMemsetAsync(prune_stats, 0, 64, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(prune stats)");
 
     // operand images as 2-D tensors [images * 128 rows, 64]: an un-swizzled box copies image rows verbatim
     CUtensorMap tmap_dy, tmap_dy_half, tmap_j_half;
@@ -258,6 +277,20 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
         const int t1 = t0 + pl.chunk_tiles < total_tiles ? t0 + pl.chunk_tiles : total_tiles;
         jp.tile_begin = bp.tile_begin = t0;
         jp.tile_end = bp.tile_end = t1;
+        if (prune) {
+            // which tiles of the chunk carry a non-negligible share of the alignment posterior?
+            ScopedTiming tm("tile_activity+compact", st);
+            const int n = t1 - t0;
+            e = launch_pdl(tile_activity_kernel, dim3((n + 7) / 8), dim3(256), 0, st, bp, alpha, beta, cost,
+                           prune_log2_eps * 0.6931471805599453f, prune_flags);
+            if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "tile_activity_kernel launch");
+            e = launch_pdl(compact_active_kernel, dim3(1), dim3(1024), 0, st, bp, (const uint8_t*)prune_flags, prune_ids, prune_stats);
+            if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "compact_active_kernel launch");
+            g_launches += 2;
+            jp.active_ids = bp.active_ids = prune_ids;
+            jp.active_count = bp.active_count = prune_stats;
+            bp.tile_flags = prune_flags;
+        }
         {
             ScopedTiming tm("joint_gemm_kernel<GRAD>", st);
             if (int rc = launch_joint<MODE_GRAD>(maps, jp, sms, st)) return rc;

@@ -55,6 +55,10 @@ struct BwdParams {
     int hu_item0[3];   // work items of h-unit u are numbered [hu_item0[u], hu_item0[u+1])
     int accumulate;    // 0: store, 1: read-modify-write (later chunks)
     long long* prof;   // development: MMA-warp cycle counters per CTA (or nullptr)
+    // backward tile pruning (nullptr / nullptr: every live tile is processed)
+    const int* active_ids;       // ordered dense ids of the chunk's active tiles
+    const int* active_count;     // their number
+    const uint8_t* tile_flags;   // [tile - tile_begin] 1 = active (what the fold of the partial rows may read)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -195,6 +199,7 @@ dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         if (!cur.seek(p, 2 * pi)) return false;
         tl0 = cur.tile(p) - p.tile_begin;
         tl1 = cur.seek(p, 2 * pi + 1) ? cur.tile(p) - p.tile_begin : -1;
+        cur.hint(p, 2 * ((unit + n_clusters) / p.NHC));  // list mode: the next unit's first id is fetched early
         return true;
     };
 
@@ -313,6 +318,88 @@ dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward tile pruning.  Every term of d cost / d logits of cell (t,u) carries the factor
+// exp(alpha(t,u) + beta(t,u) - L) (or less: the blank / emit terms are parts of it), the posterior probability that
+// the alignment passes through the cell.  Away from the band of plausible alignments it decays like a Gaussian
+// tail (1e-100 and below at config 2), so whole tiles contribute nothing that survives fp32 accumulation next to
+// the O(1) terms of the band -- let alone the bf16 rounding of dlogits.  A tile is ACTIVE when its largest
+// relative occupancy is >= 2^prune_log2_eps (default 2^-30); only active tiles are recomputed and fed to the
+// backward GEMMs.  NaN occupancies (non-finite logits) keep their tile active, so they still poison the
+// utterance's gradients as in the reference.
+// ------------------------------------------------------------------------------------------------
+// one warp per tile of the chunk: flags[tile - tile_begin] = 1 (active) / 0
+__global__ void __launch_bounds__(256)
+tile_activity_kernel(const BwdParams p, const float* __restrict__ alpha, const float* __restrict__ beta,
+                     const float* __restrict__ cost, float ln_eps, uint8_t* __restrict__ flags) {
+    griddep_wait();
+    const int lane = threadIdx.x & 31;
+    const int tl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tl >= p.tile_end - p.tile_begin) return;
+    const int tile = p.tile_begin + tl;
+    const int per_b = p.nTt * p.nTu;
+    const int b = tile / per_b, rem = tile - b * per_b;
+    const int tt = rem / p.nTu, tu = rem - tt * p.nTu;
+    const int tT = 1 << p.tT_log2, tU = kTileM >> p.tT_log2;
+    const int Tb = min(max(p.logit_lengths[b], 1), p.T), Ub = min(max(p.target_lengths[b], 0), p.U - 1) + 1;
+    bool active = false;
+    if (tt * tT < Tb && tu * tU < Ub) {  // a live tile
+        const float L = -cost[b];
+        float m = -INFINITY;
+        bool nan = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = lane + 32 * i;
+            const int t = tt * tT + (r & (tT - 1)), u = tu * tU + (r >> p.tT_log2);
+            if (t < Tb && u < Ub) {
+                const size_t o = skew_index(b, t, u, p.T, p.U);
+                const float x = alpha[o] + beta[o] - L;
+                nan |= !(x == x);
+                m = fmaxf(m, x);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        nan = __any_sync(0xffffffffu, nan);
+        active = nan || !(m < ln_eps);
+    }
+    if (lane == 0) flags[tl] = active ? 1 : 0;
+}
+
+// ordered compaction of the active tiles (single CTA): ids[0..count) = dense tile ids, stats[0] = count of this chunk,
+// stats[1] += count, stats[2] += live tiles (both cumulative over the chunks of one backward call)
+__global__ void __launch_bounds__(1024)
+compact_active_kernel(const BwdParams p, const uint8_t* __restrict__ flags, int* __restrict__ ids, int* __restrict__ stats) {
+    __shared__ int warp_sums[32];
+    __shared__ int running;
+    griddep_wait();
+    const int n = p.tile_end - p.tile_begin;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const bool f = i < n && flags[i] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) warp_sums[warp] = __popc(bal);
+        __syncthreads();
+        int off = running;
+        for (int w = 0; w < warp; ++w) off += warp_sums[w];
+        if (f) ids[off + __popc(bal & ((1u << lane) - 1u))] = p.tile_begin + i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 32; ++w) t += warp_sums[w];
+            running += t;
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
+        const int live = count_live_tiles_warp_geometric(p);
+        if (lane == 0) { stats[0] = running; stats[1] += running; stats[2] += live; }
+    }
+}
+
 // Fold the per-tile partial rows: one block row per output row, one thread per 4 consecutive h (float4).
 // blockIdx.x < n_enc_rows: d_enc row (frame-tile group gl, ti) = sum over the live label tiles of the group --
 // rows are complete inside a chunk (chunks are aligned to whole (utterance, frame-tile) groups) -> plain stores.
@@ -339,6 +426,7 @@ reduce_dpre_kernel(const BwdParams p, float* __restrict__ d_enc, float* __restri
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
             for (int tu = 0; tu < n_tu; ++tu) {
+                if (p.tile_flags && !p.tile_flags[gl * p.nTu + tu]) continue;  // pruned tile: no partial rows exist
                 const float4 x = base[(size_t)tu * tile_stride4];
                 s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
             }
@@ -357,6 +445,7 @@ reduce_dpre_kernel(const BwdParams p, float* __restrict__ d_enc, float* __restri
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
             for (int g = gb0; g < gb1; ++g) {  // dead frame tiles carry no data
+                if (p.tile_flags && !p.tile_flags[g * p.nTu + tu - p.tile_begin]) continue;  // pruned tile
                 const float4 x = base[(size_t)(g - gb0) * p.nTu * tile_stride4];
                 s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
             }
@@ -511,6 +600,7 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constan
             LiveCursor<BwdParams> cur(p, n_live);
             for (int k = it.split;; k += it.n_splits) {  // the item's share of the LIVE tiles
                 if (!cur.seek(p, k)) break;
+                cur.hint(p, k + it.n_splits);  // list mode: next id in flight while this tile's stages are issued
                 const int tl = cur.tile(p) - p.tile_begin;
                 const int dy_row0 = (tl * p.NT4 + it.vt2 * 4 + rank * 2) * 128;
                 for (int half = 0; half < 2; ++half) {

@@ -29,7 +29,9 @@ __host__ __device__ __forceinline__ size_t skew_index(int b, int t, int u, int T
 // LIVE tile, k = 0, 1, ...: per (b, tt) group either all ceil(U_b / tU) leading tiles are live or none, so a
 // cursor walking the groups finds the k-th live tile without any list in memory.  seek() is O(1) amortised for
 // non-decreasing k (it rewinds otherwise); every role of a kernel runs its own cursor and sees the same sequence.
-// P needs: logit_lengths, target_lengths, T, U, tT_log2, nTt, nTu, tile_begin, tile_end (whole groups).
+// P needs: logit_lengths, target_lengths, T, U, tT_log2, nTt, nTu, tile_begin, tile_end (whole groups), and
+// active_ids / active_count: when active_ids != nullptr the backward kernels work on that explicit, ordered list of
+// dense tile ids instead (the live tiles whose lattice occupancy is not negligible, see tile_activity_kernel).
 // ------------------------------------------------------------------------------------------
 template <typename P>
 struct LiveCursor {
@@ -38,6 +40,7 @@ struct LiveCursor {
     // tile is simply tile_begin + k and the cursor degenerates to stateless index arithmetic.
     int g, g_end, base, b, tt, tu, Tb, Ub, live_tt, n_u;
     bool dense;
+    int n_list, pf_k, pf_tile;  // list mode (n_list >= 0): number of ids, one prefetched entry
     __device__ __forceinline__ void load_utterance(const P& p) {
         // lengths are clamped to the padded lattice (validated on the host after launching)
         const int tT = 1 << p.tT_log2, tU = 128 >> p.tT_log2;
@@ -55,20 +58,33 @@ struct LiveCursor {
     }
     // n_live: count_live_tiles_warp(p) of the same range (every role computes it once, as a converged warp)
     __device__ __forceinline__ LiveCursor(const P& p, int n_live)
-        : g_end(p.tile_end / p.nTu), tu(0), dense(n_live == p.tile_end - p.tile_begin) {
-        if (dense) { g = 0; base = 0; b = -1; tt = 0; Tb = 0; Ub = 0; live_tt = 0; n_u = 0; }
+        : g_end(p.tile_end / p.nTu), tu(0), dense(n_live == p.tile_end - p.tile_begin && p.active_ids == nullptr),
+          n_list(p.active_ids ? n_live : -1), pf_k(-1), pf_tile(0) {
+        if (dense || n_list >= 0) { g = 0; base = 0; b = -1; tt = 0; Tb = 0; Ub = 0; live_tt = 0; n_u = 0; }
         else rewind(p);
+    }
+    // list mode: start fetching entry k now (the id is needed at the next seek(k); hides the load latency)
+    __device__ __forceinline__ void hint(const P& p, int k) {
+        if (n_list >= 0 && k < n_list) { pf_k = k; pf_tile = __ldg(p.active_ids + k); }
+    }
+    __device__ __forceinline__ void set_tile(const P& p, int tile) {
+        g = tile / p.nTu;
+        tu = tile - g * p.nTu;
+        const int bb = g / p.nTt;
+        tt = g - bb * p.nTt;
+        if (bb != b) { b = bb; load_utterance(p); }
     }
     // positions the cursor on the k-th live tile of [tile_begin, tile_end); false when there are fewer
     __device__ __forceinline__ bool seek(const P& p, int k) {
+        if (n_list >= 0) {
+            if (k >= n_list) return false;
+            set_tile(p, k == pf_k ? pf_tile : __ldg(p.active_ids + k));
+            return true;
+        }
         if (dense) {
             const int tile = p.tile_begin + k;
             if (tile >= p.tile_end) return false;
-            g = tile / p.nTu;
-            tu = tile - g * p.nTu;
-            const int bb = g / p.nTt;
-            tt = g - bb * p.nTt;
-            if (bb != b) { b = bb; load_utterance(p); }
+            set_tile(p, tile);
             return true;
         }
         if (k < base) rewind(p);
@@ -92,7 +108,7 @@ struct LiveCursor {
 // utterances l, l+32, ...).  Roles that only need to know HOW MANY rounds there are (MMA issue, W stream, relays)
 // use this once instead of walking a cursor on their critical path.
 template <typename P>
-__device__ __forceinline__ int count_live_tiles_warp(const P& p) {
+__device__ __forceinline__ int count_live_tiles_warp_geometric(const P& p) {
     const int lane = threadIdx.x & 31;
     const int g0 = p.tile_begin / p.nTu, g1 = p.tile_end / p.nTu;
     const int b0 = g0 / p.nTt, b1 = (g1 + p.nTt - 1) / p.nTt;
@@ -107,6 +123,11 @@ __device__ __forceinline__ int count_live_tiles_warp(const P& p) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
     return n;
+}
+template <typename P>
+__device__ __forceinline__ int count_live_tiles_warp(const P& p) {
+    if (p.active_ids) return *p.active_count;  // explicit list (backward tile pruning)
+    return count_live_tiles_warp_geometric(p);
 }
 
 enum ActKind : int { ACT_LEAKY_RELU = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_IDENTITY = 3 };

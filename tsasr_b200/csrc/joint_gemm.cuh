@@ -104,6 +104,9 @@ struct JointParams {
     // MODE_DEBUG output
     float* dbg_logits;          // [B,T,U,V]
     long long* prof;            // development: per-CTA cycle counters of the MMA lane (or nullptr)
+    // MODE_GRAD with tile pruning: ordered list of the chunk's active tiles (nullptr: every live tile)
+    const int* active_ids;
+    const int* active_count;
 };
 
 struct TileCoord { int b, t0, u0, Tb, Ub; bool live; };

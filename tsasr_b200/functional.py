@@ -219,7 +219,7 @@ class FusedJointRnnt(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, dec, W, bias, targets, logit_lengths, target_lengths, blank, act_kind, act_param,
-                max_chunk_cells):
+                max_chunk_cells, prune_log2_eps=None):
         enc16, dec16, W16 = _operands_bf16(enc.detach(), dec.detach(), W.detach())
         b32 = bias.detach().to(torch.float32).contiguous()
         B, T, _ = enc16.shape
@@ -227,26 +227,28 @@ class FusedJointRnnt(torch.autograd.Function):
         lat2, logz = ops.joint_fwd(enc16, dec16, W16, b32, targets, logit_lengths, target_lengths, blank, act_kind, act_param)
         alpha, beta, cost, _, _ = ops.alpha_beta(lat2, logit_lengths, target_lengths, B, T, U)
         ctx.save_for_backward(enc16, dec16, W16, b32, targets, logit_lengths, target_lengths, lat2, logz, alpha, beta, cost)
-        ctx.cfg = (blank, act_kind, act_param, max_chunk_cells)
+        ctx.cfg = (blank, act_kind, act_param, max_chunk_cells, prune_log2_eps)
         ctx.in_dtypes = (enc.dtype, dec.dtype, W.dtype, bias.dtype)
         return cost
 
     @staticmethod
     def backward(ctx, dcost):
         enc16, dec16, W16, b32, targets, ll, tl, lat2, logz, alpha, beta, cost = ctx.saved_tensors
-        blank, act_kind, act_param, max_chunk_cells = ctx.cfg
+        blank, act_kind, act_param, max_chunk_cells, prune_log2_eps = ctx.cfg
         dcost = dcost.to(torch.float32).contiguous()
         d_enc, d_dec, dW, db = ops.joint_bwd(enc16, dec16, W16, b32, targets, ll, tl, blank, act_kind, act_param,
-                                             lat2, logz, alpha, beta, cost, dcost, max_chunk_cells)
+                                             lat2, logz, alpha, beta, cost, dcost, max_chunk_cells, prune_log2_eps)
         de, dd, dw, dbt = ctx.in_dtypes
-        return (d_enc.to(de), d_dec.to(dd), dW.to(dw), db.to(dbt), None, None, None, None, None, None, None)
+        return (d_enc.to(de), d_dec.to(dd), dW.to(dw), db.to(dbt), None, None, None, None, None, None, None, None)
 
 
 def fused_joint_rnnt_loss(enc_out, dec_out, weight, bias, targets, logit_lengths, target_lengths, blank=0,
                           activation="leaky_relu", act_param=0.01, reduction="mean", check_lengths=True,
-                          max_chunk_cells=0, relative_lengths=False):
+                          max_chunk_cells=0, relative_lengths=False, prune_log2_eps=None):
     """Functional form of the fused path.  Lengths are absolute int32 counts, or -- with ``relative_lengths=True`` --
-    SpeechBrain's relative floats, converted bit-exactly like SB/nnet/losses.py:58-59."""
+    SpeechBrain's relative floats, converted bit-exactly like SB/nnet/losses.py:58-59.
+    ``prune_log2_eps``: backward tile pruning threshold (None: TSASR_PRUNE_LOG2_EPS or -30; >= 0: off), see
+    include/tsasr_b200.h."""
     _check_reduction(reduction)
     if enc_out.dim() != 3 or dec_out.dim() != 3:
         raise ValueError("enc_out must be [B,T,H] and dec_out [B,U,H]")
@@ -268,7 +270,7 @@ def fused_joint_rnnt_loss(enc_out, dec_out, weight, bias, targets, logit_lengths
         logit_lengths, target_lengths, stats, ready = _prepare_lengths(logit_lengths, target_lengths, T, targets.shape[1],
                                                                        relative_lengths)
         costs = FusedJointRnnt.apply(enc_out, dec_out, weight, bias, targets, logit_lengths, target_lengths, int(blank),
-                                     _lib.ACT_CODES[activation], float(act_param), int(max_chunk_cells))
+                                     _lib.ACT_CODES[activation], float(act_param), int(max_chunk_cells), prune_log2_eps)
         if check_lengths:
             # raises what torchaudio raises; the kernels above are already queued
             _DeferredLengthCheck(stats, ready).finish(T, U, targets.shape[1])

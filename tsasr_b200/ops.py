@@ -120,8 +120,29 @@ def _workspace(dev, nbytes):
     return ws
 
 
+def default_prune_log2_eps():
+    """Backward tile pruning threshold (log2 of the smallest alignment posterior a tile must reach to be kept);
+    TSASR_PRUNE_LOG2_EPS overrides the default -30, any value >= 0 switches pruning off."""
+    import os
+
+    return float(os.environ.get("TSASR_PRUNE_LOG2_EPS", "-30"))
+
+
+_last_bwd = {}
+
+
+def last_backward_tile_stats(dev=None):
+    """(active tiles, live tiles) of the last joint_bwd on ``dev`` (synchronises; measurement aid)."""
+    if dev is None:
+        dev = next(iter(_last_bwd))
+    ws, off = _last_bwd[dev]
+    base = (-ws.data_ptr()) % 1024 + off
+    st = ws[base: base + 12].view(torch.int32).tolist()
+    return st[1], st[2]
+
+
 def joint_bwd(enc, dec, W, bias, targets, logit_lengths, target_lengths, blank, act_kind, act_param,
-              lat2, logz, alpha, beta, cost, dcost, max_chunk_cells=0):
+              lat2, logz, alpha, beta, cost, dcost, max_chunk_cells=0, prune_log2_eps=None):
     """Backward of the fused chain -> (d_enc [B,T,H], d_dec [B,U,H], dW [V,H], db [V]) fp32."""
     dev = _require_cuda(enc, dec, W, bias, lat2, logz, alpha, beta, cost, dcost)
     B, T, H = enc.shape
@@ -130,6 +151,9 @@ def joint_bwd(enc, dec, W, bias, targets, logit_lengths, target_lengths, blank, 
     lib = _lib.load()
     nbytes = lib.tsasr_joint_bwd_workspace_bytes(B, T, U, H, V, int(max_chunk_cells))
     ws = _workspace(dev, max(int(nbytes), 16))
+    if prune_log2_eps is None:
+        prune_log2_eps = default_prune_log2_eps()
+    _last_bwd[dev] = (ws, int(lib.tsasr_joint_bwd_stats_offset(B, T, U, H, V, int(max_chunk_cells))))
     d_enc = torch.empty((B, T, H), dtype=torch.float32, device=dev)
     d_dec = torch.empty((B, U, H), dtype=torch.float32, device=dev)
     dW = torch.empty((V, H), dtype=torch.float32, device=dev)
@@ -138,7 +162,7 @@ def joint_bwd(enc, dec, W, bias, targets, logit_lengths, target_lengths, blank, 
         _lib.check(lib.tsasr_joint_bwd(
             _p(enc), _p(dec), _p(W), _p(bias), _p(targets), _p(logit_lengths), _p(target_lengths),
             B, T, U, H, V, int(blank), int(act_kind), float(act_param), _p(lat2), _p(logz), _p(alpha), _p(beta),
-            _p(cost), _p(dcost), _p(ws), ctypes.c_size_t(ws.numel()), int(max_chunk_cells),
+            _p(cost), _p(dcost), _p(ws), ctypes.c_size_t(ws.numel()), int(max_chunk_cells), float(prune_log2_eps),
             _p(d_enc), _p(d_dec), _p(dW), _p(db), _stream(dev)))
     return d_enc, d_dec, dW, db
 
