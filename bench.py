@@ -195,15 +195,18 @@ def run_reference(args, rank):
     }))
 
 
-def kernel_lines(kernel_ms, cells, H, V, B, T, U, peak_tf, peak_hbm):
+def kernel_lines(kernel_ms, cells, H, V, B, T, U, peak_tf, peak_hbm, active_tiles=None, live_tiles=None):
     """Per-kernel device time of one step (CUDA events inside the library, 5 extra steps after the timed region)
-    with the bound that applies: GEMM kernels against the measured bf16 peak (2*M*H*V FLOPs each), the lattice
-    DP and the fold kernels against the measured HBM copy bandwidth (algorithmic bytes)."""
+    with the bound that applies: GEMM kernels against the measured bf16 peak, the lattice DP and the fold kernels
+    against the measured HBM copy bandwidth (algorithmic bytes).  The forward GEMM is credited
+    the algorithmic 2*M*H*V; with tile pruning the three backward GEMM kernels are credited the FLOPs they EXECUTE
+    (2 * 128 * active tiles * H * V), so their fraction stays a statement about the kernel, not about the pruning."""
     gemm = 2.0 * cells * H * V
-    tiles = B * ((T + 15) // 16) * ((U + 7) // 8)
+    gemm_bwd = 2.0 * 128 * active_tiles * H * V if active_tiles else gemm
+    tiles = active_tiles if active_tiles else B * ((T + 15) // 16) * ((U + 7) // 8)
     algo = {
-        "joint_gemm_kernel<FWD>": ("tensor", gemm), "joint_gemm_kernel<GRAD>": ("tensor", gemm),
-        "dj_gemm_kernel": ("tensor", gemm), "dw_gemm_kernel": ("tensor", gemm),
+        "joint_gemm_kernel<FWD>": ("tensor", gemm), "joint_gemm_kernel<GRAD>": ("tensor", gemm_bwd),
+        "dj_gemm_kernel": ("tensor", gemm_bwd), "dw_gemm_kernel": ("tensor", gemm_bwd),
         "alpha_beta_kernel": ("hbm", 24.0 * cells),
         "reduce_dpre_kernel": ("hbm", 4.0 * (tiles * 24 * H + B * T * H + 2 * B * U * H)),
         "reduce_dw_kernel": ("hbm", 4.0 * V * H * 10),
@@ -331,6 +334,38 @@ def main():
     value = world * cells / (ms_per_step / 1e3)
     fwd_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in fwd_ev)
 
+    # ---- the same steps with backward tile pruning switched off (reported beside the headline, not instead of it) ----
+    prune_eps = ops.default_prune_log2_eps()
+    active_tiles, live_tiles = (ops.last_backward_tile_stats(dev) if prune_eps < 0 else (None, None))
+    dense_ms = None
+    if prune_eps < 0:
+        def step_dense():
+            lat2, logz = ops.joint_fwd(enc16, dec16, W16, bias, targets, ll, tl, cfg["blank"], act, cfg["act_param"])
+            alpha, beta, cost, _, _ = ops.alpha_beta(lat2, ll, tl, B, T, U)
+            ops.joint_bwd(enc16, dec16, W16, bias, targets, ll, tl, cfg["blank"], act, cfg["act_param"], lat2, logz, alpha, beta,
+                          cost, dcost, prune_log2_eps=0.0)
+            if dist is not None:
+                dist.all_reduce(comm)
+        for _ in range(3):
+            flush.zero_()
+            step_dense()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        evs_d = []
+        for _ in range(min(K, 10)):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            step_dense()
+            e.record()
+            evs_d.append((s, e))
+        torch.cuda.synchronize()
+        t = torch.tensor([sum(a.elapsed_time(b_) for a, b_ in evs_d) / len(evs_d)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dense_ms = t.item()
+
     # ---- e2e: public drop-in modules, pinned host inputs, H2D + D2H inside the timed region ----
     joiner = tsasr_b200.Transducer_joint(joint="sum", nonlinearity=torch.nn.LeakyReLU)
     head = torch.nn.Linear(H, V).to(dev)
@@ -437,8 +472,16 @@ def main():
                          "algorithmic_flops_per_launch": flops,
                          "step_frac_of_6MHV_roofline": (6.0 * cells * H * V / (ms_per_step / 1e3) / 1e12) / peak_tf},
             "clocks": clocks,
-            "kernels": kernel_lines(kernel_ms, cells, H, V, B, T, U, peak_tf, peak_hbm),
+            "kernels": kernel_lines(kernel_ms, cells, H, V, B, T, U, peak_tf, peak_hbm, active_tiles, live_tiles),
         }
+        out["config"]["backward_tile_pruning"] = (
+            {"log2_eps": prune_eps, "active_tiles": active_tiles, "live_tiles": live_tiles,
+             "what": "128-cell tiles whose largest alignment posterior exp(alpha+beta-L) < 2^log2_eps are left out of the "
+                     "backward (every dlogits term carries that factor; below fp32 resolution of the kept terms); "
+                     "TSASR_PRUNE_LOG2_EPS=0 switches it off"} if prune_eps < 0 else "off")
+        if dense_ms is not None:
+            out["dense_backward"] = {"ms_per_step": dense_ms, "value": world * cells / (dense_ms / 1e3), "unit": UNIT,
+                                     "what": "same steps with tile pruning off (every live tile recomputed and fed to the GEMMs)"}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, secs = cpu_reference_step(CPU_SAMPLE, threads)
