@@ -199,7 +199,7 @@ dj_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         if (!cur.seek(p, 2 * pi)) return false;
         tl0 = cur.tile(p) - p.tile_begin;
         tl1 = cur.seek(p, 2 * pi + 1) ? cur.tile(p) - p.tile_begin : -1;
-        cur.hint(p, 2 * ((unit + n_clusters) / p.NHC));  // list mode: the next unit's first id is fetched early
+        cur.hint_pair(p, 2 * ((unit + n_clusters) / p.NHC));  // list mode: the next unit's ids are fetched early
         return true;
     };
 

@@ -40,7 +40,7 @@ struct LiveCursor {
     // tile is simply tile_begin + k and the cursor degenerates to stateless index arithmetic.
     int g, g_end, base, b, tt, tu, Tb, Ub, live_tt, n_u;
     bool dense;
-    int n_list, pf_k, pf_tile;  // list mode (n_list >= 0): number of ids, one prefetched entry
+    int n_list, pf_k, pf_tile, pf_tile1;  // list mode (n_list >= 0): number of ids, prefetched entries pf_k and pf_k + 1
     __device__ __forceinline__ void load_utterance(const P& p) {
         // lengths are clamped to the padded lattice (validated on the host after launching)
         const int tT = 1 << p.tT_log2, tU = 128 >> p.tT_log2;
@@ -59,13 +59,22 @@ struct LiveCursor {
     // n_live: count_live_tiles_warp(p) of the same range (every role computes it once, as a converged warp)
     __device__ __forceinline__ LiveCursor(const P& p, int n_live)
         : g_end(p.tile_end / p.nTu), tu(0), dense(n_live == p.tile_end - p.tile_begin && p.active_ids == nullptr),
-          n_list(p.active_ids ? n_live : -1), pf_k(-1), pf_tile(0) {
+          n_list(p.active_ids ? n_live : -1), pf_k(-2), pf_tile(0), pf_tile1(0) {
         if (dense || n_list >= 0) { g = 0; base = 0; b = -1; tt = 0; Tb = 0; Ub = 0; live_tt = 0; n_u = 0; }
         else rewind(p);
     }
     // list mode: start fetching entry k now (the id is needed at the next seek(k); hides the load latency)
     __device__ __forceinline__ void hint(const P& p, int k) {
-        if (n_list >= 0 && k < n_list) { pf_k = k; pf_tile = __ldg(p.active_ids + k); }
+        if (n_list >= 0 && k < n_list) { pf_k = k; pf_tile = __ldg(p.active_ids + k); pf_tile1 = -1; }
+    }
+    // same for the entries k and k + 1 of a tile pair (k even: one 8-byte load)
+    __device__ __forceinline__ void hint_pair(const P& p, int k) {
+        if (n_list >= 0 && k + 1 < n_list) {
+            const int2 v = __ldg(reinterpret_cast<const int2*>(p.active_ids + k));
+            pf_k = k; pf_tile = v.x; pf_tile1 = v.y;
+        } else {
+            hint(p, k);
+        }
     }
     __device__ __forceinline__ void set_tile(const P& p, int tile) {
         g = tile / p.nTu;
@@ -78,7 +87,7 @@ struct LiveCursor {
     __device__ __forceinline__ bool seek(const P& p, int k) {
         if (n_list >= 0) {
             if (k >= n_list) return false;
-            set_tile(p, k == pf_k ? pf_tile : __ldg(p.active_ids + k));
+            set_tile(p, k == pf_k ? pf_tile : (k == pf_k + 1 && pf_tile1 >= 0) ? pf_tile1 : __ldg(p.active_ids + k));
             return true;
         }
         if (dense) {

@@ -138,6 +138,9 @@ struct Rounds {
         if (!cur.seek(p, k0)) return false;
         tc.live = true;
         if (PAIR && rank) tc.live = cur.seek(p, k0 + 1);
+        // list mode (pruned backward): the ids of this unit's NEXT round are fetched now, off the critical path
+        if (PAIR) cur.hint_pair(p, 2 * next_round);
+        else cur.hint(p, next_round);
         if (tc.live) {
             my_tile = cur.tile(p);
             tc.b = cur.b;
