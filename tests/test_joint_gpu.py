@@ -303,3 +303,36 @@ def test_backward_tile_pruning_is_invisible_in_fp32():
     assert 0 < st1[0] < 0.85 * st1[1], st1                 # the far corners of the lattice are skipped
     for a, c in zip(dense, pruned):
         assert _rel_err(c, a) < 1e-5
+
+
+def test_fused_path_fuzz_vs_compat_path():
+    """Random shapes, ragged lengths, activations, chunk sizes: the fused tcgen05 path (tile pruning on) against the
+    compat kernels (materialised logits built by torch from the same bf16-rounded operands; themselves pinned on the
+    C oracle and the golden vectors in test_lattice_gpu.py).  Loss 1e-4 relative, gradients 1e-2 of their largest entry."""
+    from oracle.reference_chain import reference_joint_logits
+
+    d = _dev()
+    rng = np.random.default_rng(2024)
+    acts = ["leaky_relu", "relu", "tanh", "identity"]
+    for case in range(24):
+        B = int(rng.integers(1, 5))
+        T = int(rng.integers(1, 90))
+        U = int(rng.integers(1, 45))
+        H = 64 * int(rng.integers(1, 11))
+        V = int(rng.integers(2, 1100))
+        act = acts[case % 4]
+        enc, dec, W, b, targets, ll, tl = _inputs(B, T, U, H, V, seed=1000 + case)
+        dcost = torch.tensor(rng.uniform(0.2, 2.0, B), dtype=torch.float32)
+        chunk = 0 if case % 3 else 128 * int(rng.integers(1, 9))
+        e, dc, w, bb = (x.to(d).float().requires_grad_() for x in (enc, dec, W, b))
+        costs = tsasr_b200.fused_joint_rnnt_loss(e, dc, w, bb, targets.to(d), ll.to(d), tl.to(d), blank=0, activation=act,
+                                                 reduction="none", max_chunk_cells=chunk)
+        (costs * dcost.to(d)).sum().backward()
+        e2, dc2, w2, bb2 = (x.to(d).float().requires_grad_() for x in (enc, dec, W, b))
+        logits = reference_joint_logits(e2, dc2, w2, bb2, act, 0.01, round_bf16=True)
+        costs2 = tsasr_b200.rnnt_loss(logits.contiguous(), targets.to(d), ll.to(d), tl.to(d), blank=0, reduction="none")
+        (costs2 * dcost.to(d)).sum().backward()
+        tag = f"case {case}: B={B} T={T} U={U} H={H} V={V} act={act} chunk={chunk}"
+        np.testing.assert_allclose(costs.detach().cpu().numpy(), costs2.detach().cpu().numpy(), rtol=LOSS_RTOL, err_msg=tag)
+        for got, ref, name in ((e.grad, e2.grad, "d_enc"), (dc.grad, dc2.grad, "d_dec"), (w.grad, w2.grad, "dW"), (bb.grad, bb2.grad, "db")):
+            assert _rel_err(got, ref) < GRAD_REL, (tag, name, _rel_err(got, ref))
