@@ -407,7 +407,8 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
     (void)tU;
     {
         ScopedTiming tm("reduce_dw_kernel", st);
-        e = launch_pdl(reduce_dw_kernel, dim3(sms * 2), dim3(256), 0, st, bp, dW, db);
+        const int dw_blocks = (int)(((size_t)V * H / 4 + 255) / 256);
+        e = launch_pdl(reduce_dw_kernel, dim3(dw_blocks < sms * 8 ? dw_blocks : sms * 8), dim3(256), 0, st, bp, dW, db);
     }
     ++g_launches;
     if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "reduce_dw_kernel launch");

@@ -730,16 +730,23 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constan
     }
 }
 
-__global__ void reduce_dw_kernel(const BwdParams p, float* __restrict__ dW, float* __restrict__ db) {
+__global__ void __launch_bounds__(256)
+reduce_dw_kernel(const BwdParams p, float* __restrict__ dW, float* __restrict__ db) {
     griddep_wait();
     const size_t vrows = (size_t)p.NV2 * 256;
-    const size_t n = (size_t)p.V * p.H;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int h = (int)(i % p.H);
+    const size_t n4 = (size_t)p.V * p.H / 4;  // H % 64 == 0: a float4 never straddles rows or h-units
+    const float4* part = reinterpret_cast<const float4*>(p.dW_part);
+    const size_t split_stride4 = vrows * p.H / 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const int h = (int)((i * 4) % p.H);
         const int ns = p.hu_splits[(p.NHU > 1 && h >= p.hu_blk[1] * 64) ? 1 : 0];
-        float s = 0.f;
-        for (int sp = 0; sp < ns; ++sp) s += p.dW_part[(size_t)sp * vrows * p.H + i];
-        dW[i] = s;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int sp = 0; sp < ns; ++sp) {
+            const float4 x = part[(size_t)sp * split_stride4 + i];
+            s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+        }
+        reinterpret_cast<float4*>(dW)[i] = s;
     }
     const int ns_db = p.hu_splits[p.NHU - 1];
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < (size_t)p.V; v += (size_t)gridDim.x * blockDim.x) {
