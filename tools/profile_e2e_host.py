@@ -47,4 +47,4 @@ pr.enable()
 for _ in range(20):
     step()
 pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+pstats.Stats(pr).sort_stats("tottime").print_stats(30)

@@ -266,7 +266,7 @@ def fused_joint_rnnt_loss(enc_out, dec_out, weight, bias, targets, logit_lengths
     if not 0 <= blank < V:
         raise RuntimeError("blank must be within [0, logits.shape[-1])")
     targets = targets.to(torch.int32).contiguous()
-    with torch.cuda.device(enc_out.device):
+    with ops._on_device(enc_out.device):
         logit_lengths, target_lengths, stats, ready = _prepare_lengths(logit_lengths, target_lengths, T, targets.shape[1],
                                                                        relative_lengths)
         costs = FusedJointRnnt.apply(enc_out, dec_out, weight, bias, targets, logit_lengths, target_lengths, int(blank),

@@ -21,6 +21,22 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class _on_device:
+    """``with torch.cuda.device(dev)`` only when ``dev`` is not already current (the context manager costs ~10 us of
+    host time per call, which is exposed in front of the first kernel of a step)."""
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
 def _require_cuda(*tensors):
     dev = None
     for t in tensors:
@@ -46,7 +62,7 @@ def logits_to_lattice(logits, targets, logit_lengths, target_lengths, blank, nor
     n = lattice_elems(B, T, U)
     lat2 = torch.empty((n, 2), dtype=torch.float32, device=dev)
     den = torch.empty((n,), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _lib.check(_lib.load().tsasr_logits_to_lattice(
             _p(logits), _DTYPE_CODE[logits.dtype], _p(targets), _p(logit_lengths), _p(target_lengths),
             B, T, U, V, int(blank), int(bool(normalized)), _p(lat2), _p(den), _stream(dev)))
@@ -57,10 +73,9 @@ def alpha_beta(lat2, logit_lengths, target_lengths, B, T, U):
     """Wavefront DP -> (alpha, beta [cells] fp32, cost [B] = -log P, ll_alpha [B], ll_beta [B])."""
     dev = _require_cuda(lat2, logit_lengths, target_lengths)
     n = lattice_elems(B, T, U)
-    alpha = torch.empty((n,), dtype=torch.float32, device=dev)
-    beta = torch.empty((n,), dtype=torch.float32, device=dev)
-    out = torch.empty((3, B), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    buf = torch.empty((2 * n + 3 * B,), dtype=torch.float32, device=dev)  # one allocation: alpha | beta | cost, ll_a, ll_b
+    alpha, beta, out = buf[:n], buf[n: 2 * n], buf[2 * n:].view(3, B)
+    with _on_device(dev):
         _lib.check(_lib.load().tsasr_lattice_alpha_beta(
             _p(lat2), _p(logit_lengths), _p(target_lengths), B, T, U, _p(alpha), _p(beta),
             _p(out[0]), _p(out[1]), _p(out[2]), _stream(dev)))
@@ -71,7 +86,7 @@ def logits_grad(logits, targets, logit_lengths, target_lengths, blank, lat2, den
     dev = _require_cuda(logits, lat2, den, alpha, beta, cost, dcost)
     B, T, U, V = logits.shape
     dlogits = torch.empty_like(logits)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _lib.check(_lib.load().tsasr_logits_grad(
             _p(logits), _DTYPE_CODE[logits.dtype], _p(targets), _p(logit_lengths), _p(target_lengths),
             B, T, U, V, int(blank), _p(lat2), _p(den), _p(alpha), _p(beta), _p(cost), _p(dcost),
@@ -83,7 +98,7 @@ def logprobs_grad(shape, targets, logit_lengths, target_lengths, blank, lat2, al
     dev = _require_cuda(lat2, alpha, beta, cost, dcost)
     B, T, U, V = shape
     grads = torch.empty(shape, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _lib.check(_lib.load().tsasr_logprobs_grad(
             _p(targets), _p(logit_lengths), _p(target_lengths), B, T, U, V, int(blank), _p(lat2), _p(alpha),
             _p(beta), _p(cost), _p(dcost), _p(grads), _stream(dev)))
@@ -97,9 +112,9 @@ def joint_fwd(enc, dec, W, bias, targets, logit_lengths, target_lengths, blank, 
     U = dec.shape[1]
     V = W.shape[0]
     n = lattice_elems(B, T, U)
-    lat2 = torch.empty((n, 2), dtype=torch.float32, device=dev)
-    logz = torch.empty((n,), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    buf = torch.empty((3 * n,), dtype=torch.float32, device=dev)  # one allocation: lat2 | logz
+    lat2, logz = buf[: 2 * n].view(n, 2), buf[2 * n:]
+    with _on_device(dev):
         _lib.check(_lib.load().tsasr_joint_fwd(
             _p(enc), _p(dec), _p(W), _p(bias), _p(targets), _p(logit_lengths), _p(target_lengths),
             B, T, U, H, V, int(blank), int(act_kind), float(act_param), _p(lat2), _p(logz), _stream(dev)))
@@ -158,7 +173,7 @@ def joint_bwd(enc, dec, W, bias, targets, logit_lengths, target_lengths, blank, 
     d_dec = torch.empty((B, U, H), dtype=torch.float32, device=dev)
     dW = torch.empty((V, H), dtype=torch.float32, device=dev)
     db = torch.empty((V,), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _lib.check(lib.tsasr_joint_bwd(
             _p(enc), _p(dec), _p(W), _p(bias), _p(targets), _p(logit_lengths), _p(target_lengths),
             B, T, U, H, V, int(blank), int(act_kind), float(act_param), _p(lat2), _p(logz), _p(alpha), _p(beta),
@@ -174,7 +189,7 @@ def joint_debug_logits(enc, dec, W, bias, act_kind, act_param):
     U = dec.shape[1]
     V = W.shape[0]
     out = torch.zeros((B, T, U, V), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _lib.check(_lib.load().tsasr_joint_debug_logits(
             _p(enc), _p(dec), _p(W), _p(bias), B, T, U, H, V, int(act_kind), float(act_param), _p(out), _stream(dev)))
     return out
