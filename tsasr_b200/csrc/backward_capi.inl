@@ -1,11 +1,12 @@
 // backward_capi.inl -- tsasr_joint_bwd: chunked backward of the fused joint (included by capi.cu).
 //
-// Per chunk of cell tiles (sized to stay L2-resident, aligned to whole (utterance, frame-tile) groups):
+// Per chunk of cell tiles (a bounded workspace of operand images, aligned to whole (utterance, frame-tile) groups):
+//   0. tile_activity_kernel + compact_active_kernel  (tile pruning on) ordered list of the tiles that matter
 //   1. joint_gemm_kernel<MODE_GRAD>  recompute logits, emit bf16 dlogits + J operand images
-//   2. dj_gemm_kernel                dJ = dlogits * W, act', in-tile broadcast sums -> partial rows
-//   3. reduce_dpre_{enc,dec}_kernel  fold partial rows into d_enc / d_dec (deterministic)
+//   2. dj_gemm_kernel                dJ^T = W^T * dlogits^T, act', in-register broadcast sums -> partial rows
+//   3. reduce_dpre_kernel            fold partial rows into d_enc / d_dec (deterministic)
 //   4. dw_gemm_kernel                dW/db split-K partials (+= across chunks, plain RMW, deterministic)
-// and a final reduce_dw_kernel over the split-K partials.
+// and a final reduce_dw_kernel over the split-K partials.  All launches are chained with programmatic dependent launch.
 
 namespace {
 

@@ -1,18 +1,20 @@
 // backward_gemm.cuh -- the two backward GEMMs of the fused joint (tcgen05 + TMEM + TMA/bulk copies).
 //
-// They consume the operand images the MODE_GRAD pass of joint_gemm.cuh leaves in the (L2-sized)
-// chunk workspace: per 128-cell tile, dY images [v-block][128 cells x 64 v] and J images
-// [h-block][128 cells x 64 h], both bf16 in the SWIZZLE_128B shared-memory image, so a block is one
-// contiguous 16 KB bulk copy and is directly addressable by a UMMA descriptor -- K-major when the
-// 64-wide dimension is the contraction (dJ), MN-major when the 128 cells are the contraction (dW).
+// They consume the operand images the MODE_GRAD pass of joint_gemm.cuh leaves in the chunk workspace: per
+// 128-cell tile, dY images [v-block][128 cells x 64 v] and J images [h-block][128 cells x 64 h], both bf16 in
+// the SWIZZLE_128B shared-memory image, so an un-swizzled TMA box copies image rows verbatim and the block is
+// directly addressable by a UMMA descriptor -- K-major when the 64-wide dimension is the contraction (dJ),
+// MN-major when the 128 cells are the contraction (dW).  Both kernels run on CTA pairs (cta_group::2) and walk
+// the live -- or, with tile pruning, the active -- tiles only (LiveCursor, common.cuh).
 //
-//   dj_gemm_kernel : dJ[cells, h] = sum_v dY[cells, v] * W[v, h]          (autograd of SB/nnet/linear.py:74)
-//                    epilogue: dpre = dJ * act'(J) (transducer_joint.py:95 backward) and the two
+//   dj_gemm_kernel : dJ^T[h, cells] = sum_v W[v, h] * dY[cells, v]          (autograd of SB/nnet/linear.py:74)
+//                    epilogue: dpre = dJ * act'(enc + dec) (transducer_joint.py:95 backward) and the two
 //                    broadcast-sum reductions of transducer_joint.py:74 (sum over u -> d_enc rows,
-//                    sum over t -> d_dec rows) inside the tile; per-tile partial rows go to a small
-//                    buffer that reduce_dpre_* kernels fold deterministically.
+//                    sum over t -> d_dec rows) as in-register adds; per-tile partial rows go to a small
+//                    buffer that reduce_dpre_kernel folds deterministically.
 //   dw_gemm_kernel : dW[v, h] += sum_cells dY[cells, v] * J[cells, h], db[v] += sum_cells dY[cells, v]
-//                    (db rides along as 16 extra accumulator columns fed by a constant "ones" block).
+//                    (db rides along as 32 extra accumulator columns fed by a constant "ones" block).
+//   tile_activity_kernel / compact_active_kernel : backward tile pruning.
 #pragma once
 
 #include <cuda.h>

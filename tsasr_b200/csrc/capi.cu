@@ -205,7 +205,7 @@ static int fill_joint_params(JointParams& p, const void* enc, const void* dec, c
 
 struct JointMaps { CUtensorMap w; };
 
-// W [V,H]: 64-byte swizzled k-slices of 256 rows; enc [B*T,H] / dec [B*U,H]: plain [rows x 64] slices
+// W [V,H] as k-slices: pairs [128 v x 64 h] SWIZZLE_128B per CTA, single CTA [256 v x 32 h] SWIZZLE_64B
 static int make_joint_maps(JointMaps* m, const JointParams& p, const void* enc, const void* dec, const void* W) {
     const int tT = 1 << p.tT_log2, tU = 128 >> p.tT_log2;
     if (use_pair()) {
