@@ -216,6 +216,54 @@ def test_drop_in_modules_vs_golden(golden, name):
         assert _rel_err(got.cpu(), torch.tensor(g[key])) < GRAD_REL, key
 
 
+@pytest.mark.parametrize("reduction", ["mean", "sum", "none"])
+@pytest.mark.parametrize("entry", ["transducer_loss", "TransducerLoss"])
+def test_numba_semantics_through_the_handle_stay_fused(entry, reduction):
+    """``use_torchaudio=False`` / ``TransducerLoss`` on a deferred handle: value reduce_b(-log P_b / T_b) and the
+    un-normalised gradient of the reference's Numba branch (SB/nnet/loss/transducer_loss.py:104-106,280-293), computed
+    by the fused kernels.  Checked against (1) the materialised Numba-semantics path (itself pinned on golden vectors
+    produced by the reference's own kernels) and (2) the CPU reference chain with d cost_b = 1."""
+    B, T, U, H, V = 3, 28, 11, 128, 60
+    enc, dec, W, b, targets, ll, tl = _inputs(B, T, U, H, V, seed=4242)
+    d = _dev()
+    joiner = tsasr_b200.Transducer_joint(joint="sum", nonlinearity=torch.nn.LeakyReLU)
+
+    def run(fused):
+        e = enc.float().to(d).requires_grad_()
+        dc = dec.float().to(d).requires_grad_()
+        head = torch.nn.Linear(H, V).to(d)
+        with torch.no_grad():
+            head.weight.copy_(W.float())
+            head.bias.copy_(b)
+        logits = head(joiner(e[..., None, :], dc[:, None, ...]))
+        assert isinstance(logits, tsasr_b200.JointHandle)
+        if not fused:
+            logits = logits.materialize()
+        if entry == "TransducerLoss":
+            loss = tsasr_b200.TransducerLoss(blank=0, reduction=reduction)(logits, targets.to(d), ll.to(d), tl.to(d))
+        else:
+            loss = tsasr_b200.transducer_loss(logits, targets.to(d), (ll.float() / T).to(d), (tl.float() / (U - 1)).to(d),
+                                              blank_index=0, reduction=reduction, use_torchaudio=False)
+        gout = torch.arange(1, B + 1, dtype=torch.float32, device=d) if reduction == "none" else None
+        loss.backward(gout)
+        return loss.detach().cpu(), [x.grad.cpu() for x in (e, dc, head.weight, head.bias)]
+
+    if entry == "transducer_loss":  # relative lengths must convert back to the same integers
+        assert torch.equal(((ll.float() / T) * T).round().int(), ll) and torch.equal(((tl.float() / (U - 1)) * (U - 1)).round().int(), tl)
+    loss_f, grads_f = run(True)
+    loss_m, grads_m = run(False)
+    np.testing.assert_allclose(loss_f.numpy(), loss_m.numpy(), rtol=LOSS_RTOL)
+    for a, c in zip(grads_f, grads_m):
+        assert _rel_err(a, c) < GRAD_REL
+    dcost = torch.arange(1, B + 1, dtype=torch.float32) if reduction == "none" else torch.ones(B)
+    ref = reference_joint_loss_fwd_bwd(enc, dec, W, b, targets, ll, tl, 0, "leaky_relu", 0.01, round_bf16=True, dcost=dcost)
+    per_utt = ref["costs"] / ll.float()
+    want = {"mean": per_utt.mean(), "sum": per_utt.sum(), "none": per_utt}[reduction]
+    np.testing.assert_allclose(loss_f.numpy(), want.numpy(), rtol=LOSS_RTOL)
+    for got, key in zip(grads_f, ("d_enc", "d_dec", "dW", "db")):
+        assert _rel_err(got, ref[key]) < GRAD_REL, key
+
+
 def test_fused_length_precondition_errors_are_raised_after_safe_launch():
     """The fused path validates lengths on a side stream AFTER queueing its kernels (they clamp every length to the
     padded lattice): the same RuntimeErrors as torchaudio must come out and the device must stay healthy."""

@@ -242,14 +242,41 @@ class FusedJointRnnt(torch.autograd.Function):
         return (d_enc.to(de), d_dec.to(dd), dW.to(dw), db.to(dbt), None, None, None, None, None, None, None, None)
 
 
+class _NumbaReduce(torch.autograd.Function):
+    """``reduce_b(cost_b / T_b)`` with the backward of the reference's Numba path: ``Transducer.backward``
+    (SB/nnet/loss/transducer_loss.py:289-293) multiplies the stored per-utterance gradients by ``grad_output`` viewed as
+    [-1,1,1,1] -- the reduction and the division by T_b (:104-106, :280-287) happen inside its forward and are NOT
+    differentiated.  So d loss / d cost_b := grad_output (broadcast), whatever the reduction."""
+
+    @staticmethod
+    def forward(ctx, costs, T, reduction):
+        ctx.n = costs.shape[0]
+        per_utt = costs / T.to(torch.float32)
+        if reduction == "mean":
+            return per_utt.mean()
+        elif reduction == "sum":
+            return per_utt.sum()
+        elif reduction == "none":
+            return per_utt
+        else:
+            raise Exception("Unexpected reduction {}".format(reduction))
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output.reshape(-1).to(torch.float32).expand(ctx.n), None, None
+
+
 def fused_joint_rnnt_loss(enc_out, dec_out, weight, bias, targets, logit_lengths, target_lengths, blank=0,
                           activation="leaky_relu", act_param=0.01, reduction="mean", check_lengths=True,
-                          max_chunk_cells=0, relative_lengths=False, prune_log2_eps=None):
+                          max_chunk_cells=0, relative_lengths=False, prune_log2_eps=None, numba_semantics=False):
     """Functional form of the fused path.  Lengths are absolute int32 counts, or -- with ``relative_lengths=True`` --
     SpeechBrain's relative floats, converted bit-exactly like SB/nnet/losses.py:58-59.
     ``prune_log2_eps``: backward tile pruning threshold (None: TSASR_PRUNE_LOG2_EPS or -30; >= 0: off), see
-    include/tsasr_b200.h."""
-    _check_reduction(reduction)
+    include/tsasr_b200.h.
+    ``numba_semantics``: value and gradient scale of the reference's Numba branch (``use_torchaudio=False`` /
+    ``TransducerLoss``): ``reduce_b(-log P_b / T_b)``, gradient of ``sum_b -log P_b`` times the incoming grad_output."""
+    if not numba_semantics:
+        _check_reduction(reduction)
     if enc_out.dim() != 3 or dec_out.dim() != 3:
         raise ValueError("enc_out must be [B,T,H] and dec_out [B,U,H]")
     B, T, H = enc_out.shape
@@ -274,4 +301,6 @@ def fused_joint_rnnt_loss(enc_out, dec_out, weight, bias, targets, logit_lengths
         if check_lengths:
             # raises what torchaudio raises; the kernels above are already queued
             _DeferredLengthCheck(stats, ready).finish(T, U, targets.shape[1])
+    if numba_semantics:
+        return _NumbaReduce.apply(costs, logit_lengths, reduction)
     return _reduce(costs, reduction)

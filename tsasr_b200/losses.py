@@ -14,6 +14,7 @@ from . import functional as F
 from .transducer_joint import JointHandle
 
 Transducer = F.NumbaSemanticsTransducer
+_CODE_TO_NAME = {0: "leaky_relu", 1: "relu", 2: "tanh", 3: "identity"}
 
 
 def transducer_loss(logits, targets, input_lens, target_lens, blank_index, reduction="mean", use_torchaudio=True):
@@ -35,10 +36,10 @@ def transducer_loss(logits, targets, input_lens, target_lens, blank_index, reduc
         True  -> torchaudio semantics (what the recipe runs): reduce_b(-log P_b), exact gradient.
         False -> the SpeechBrain Numba semantics: reduce_b(-log P_b / T_b), un-normalised gradient.
     """
-    if isinstance(logits, JointHandle) and logits.has_head and use_torchaudio:
+    if isinstance(logits, JointHandle) and logits.has_head:
+        # fused path, both semantics: torchaudio's (what the recipe runs) and the Numba branch's (losses.py:81-85)
         enc = logits._enc.squeeze(2)   # [B,T,1,H] -> [B,T,H]
         dec = logits._dec.squeeze(1)   # [B,1,U,H] -> [B,U,H]
-        code_to_name = {0: "leaky_relu", 1: "relu", 2: "tanh", 3: "identity"}
         dev = enc.device
         fp32_lens = input_lens.dtype == torch.float32 and target_lens.dtype == torch.float32
         if not fp32_lens:  # unusual dtypes: the reference's own expression decides the rounding
@@ -47,8 +48,9 @@ def transducer_loss(logits, targets, input_lens, target_lens, blank_index, reduc
         # fp32 relative lengths: the conversion of losses.py:58-59 runs, bit-exact, inside tsasr_prepare_lengths
         return F.fused_joint_rnnt_loss(
             enc, dec, logits._weight, logits._bias, targets.to(dev), input_lens.to(dev), target_lens.to(dev),
-            blank=blank_index, activation=code_to_name[logits._act_code], act_param=logits._act_param,
-            reduction=reduction, relative_lengths=fp32_lens)
+            blank=blank_index, activation=_CODE_TO_NAME[logits._act_code], act_param=logits._act_param,
+            reduction=reduction, relative_lengths=fp32_lens, numba_semantics=not use_torchaudio,
+            check_lengths=use_torchaudio)  # the Numba branch has no length preconditions (the kernels clamp)
 
     # integer length conversion, bit-exact with losses.py:58-59 (fp32 multiply, round-half-even, int32)
     input_lens = (input_lens * logits.shape[1]).round().int()
@@ -78,6 +80,12 @@ class TransducerLoss(Module):
 
     def forward(self, logits, labels, T, U):
         if all(t.is_cuda for t in (logits, labels, T, U)):
+            if isinstance(logits, JointHandle) and logits.has_head:
+                # fused path with the Numba branch's value / gradient scale; T, U are absolute int32 here
+                return F.fused_joint_rnnt_loss(
+                    logits._enc.squeeze(2), logits._dec.squeeze(1), logits._weight, logits._bias, labels, T, U,
+                    blank=self.blank, activation=_CODE_TO_NAME[logits._act_code], act_param=logits._act_param,
+                    reduction=self.reduction, numba_semantics=True, check_lengths=False)
             if isinstance(logits, JointHandle):
                 logits = logits.materialize()
             log_probs = logits.log_softmax(-1)
