@@ -235,8 +235,8 @@ static int launch_joint_impl(const JointMaps& maps, const JointParams& p, int nu
     JointParams pp = p;
     long long* d_prof = nullptr;
     if (prof_on) {
-        cudaMalloc(&d_prof, sizeof(long long) * 8 * grid);
-        cudaMemset(d_prof, 0, sizeof(long long) * 8 * grid);
+        cudaMalloc(&d_prof, sizeof(long long) * 16 * grid);
+        cudaMemset(d_prof, 0, sizeof(long long) * 16 * grid);
         pp.prof = d_prof;
     }
     cudaLaunchConfig_t cfg;
@@ -259,15 +259,20 @@ static int launch_joint_impl(const JointMaps& maps, const JointParams& p, int nu
     if (e != cudaSuccess) return cuda_fail(e, "joint_gemm_kernel launch");
     if (prof_on) {
         cudaStreamSynchronize(st);
-        long long* h = new long long[8 * grid];
-        cudaMemcpy(h, d_prof, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
+        long long* h = new long long[16 * grid];
+        cudaMemcpy(h, d_prof, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost);
         double tot = 0, acc = 0, a = 0, w = 0, rounds = 0, lsum = 0, lcnt = 0, tcom = 0;
         int n = 0;
         for (int i = 0; i < grid; ++i)
-            if (h[8 * i] > 0) { tot += h[8 * i]; acc += h[8 * i + 1]; a += h[8 * i + 2]; w += h[8 * i + 3]; rounds += h[8 * i + 4]; lsum += h[8 * i + 5]; lcnt += h[8 * i + 6]; tcom += h[8 * i + 7]; ++n; }
+            if (h[16 * i] > 0) { tot += h[16 * i]; acc += h[16 * i + 1]; a += h[16 * i + 2]; w += h[16 * i + 3]; rounds += h[16 * i + 4]; lsum += h[16 * i + 5]; lcnt += h[16 * i + 6]; tcom += h[16 * i + 7]; ++n; }
         if (lcnt > 0) fprintf(stderr, "[tsasr prof] MMA issue blocks: %.0f stages per cta, %.0f cycles to issue the 4 MMAs of a stage, %.0f cycles in commits per stage\n", lcnt / n, lsum / lcnt, tcom / lcnt);
         fprintf(stderr, "[tsasr prof] mode=%d pair=%d issuing ctas=%d rounds/cta=%.1f cycles/cta=%.0f wait: acc_empty=%.1f%% a_full=%.1f%% w_full=%.1f%% other=%.1f%%  cycles/round=%.0f\n",
                 MODE, (int)PAIR, n, rounds / n, tot / n, 100 * acc / tot, 100 * a / tot, 100 * w / tot, 100 * (tot - acc - a - w) / tot, tot / rounds);
+        for (int g = 0; g < 2; ++g) {  // epilogue warp 0 of each column group, averaged over all CTAs (builds with -DTSASR_EPI_PROF)
+            double ew = 0, ep = 0, eb = 0, en = 0;
+            for (int i = 0; i < grid; ++i) { ew += h[16 * i + 8 + 4 * g]; ep += h[16 * i + 9 + 4 * g]; eb += h[16 * i + 10 + 4 * g]; en += h[16 * i + 11 + 4 * g]; }
+            if (en > 0) fprintf(stderr, "[tsasr prof] epilogue group %d, cycles per vocabulary tile: wait acc_full=%.0f process+release=%.0f bias barriers=%.0f\n", g, ew / en, ep / en, eb / en);
+        }
         delete[] h;
         cudaFree(d_prof);
     }

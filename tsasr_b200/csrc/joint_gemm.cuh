@@ -407,7 +407,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                             const uint32_t w_lo = w_lo0 + stage * (kWStageBytes >> 4);
                             if (p.prof) tm = clock64();
                             // four K = 16 MMAs: 32 bytes per step along the 128-byte swizzled rows
-                            umma_bf16_2cta_x4_e(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)w_hi << 32) | w_lo, idesc, kb != 0);
+                            if (!(p.dbg_skip & 32)) umma_bf16_2cta_x4_e(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)w_hi << 32) | w_lo, idesc, kb != 0);
                             if (p.prof) { l_sum += clock64() - tm; ++l_cnt; }
                             if (p.prof) tm = clock64();
                             if (!(p.dbg_skip & 4)) umma_commit_2cta_e(&w_empty[stage], 1);  // only the leader refills
@@ -436,7 +436,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                 ++it;
             }
             if (p.prof && lane == 0) {
-                long long* o = p.prof + blockIdx.x * 8;
+                long long* o = p.prof + blockIdx.x * 16;
                 o[0] = clock64() - t_begin; o[1] = t_acc; o[2] = t_a; o[3] = t_w; o[4] = it; o[5] = l_sum; o[6] = l_cnt; o[7] = t_commit[0];
             }
         } else if (PAIR) {
@@ -489,6 +489,9 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
         float* bias_g = bias_s + grp * kTileN;  // this group's 128 staged bias values (second half of the slot unused)
         constexpr int kGrpCols = kTileN / 2;
         uint32_t acc_it = 0, it = 0;
+#ifdef TSASR_EPI_PROF
+        long long pe_wait = 0, pe_proc = 0, pe_bar = 0, pe_t = 0;  // development build: cycle split of this warp
+#endif
         float nb0 = 0.f;  // prefetched bias value of the next vocabulary tile
         int nb_nt = -1;
         // the partner CTA releases accumulators on a local barrier that its relay warp forwards to the leader
@@ -548,6 +551,9 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                 // loaded into registers while the group's previous tile was being processed, so the L2
                 // latency of the load is off the critical path.
                 const int vt = nt;
+#ifdef TSASR_EPI_PROF
+                if (p.prof) pe_t = clock64();
+#endif
                 {
                     if (nb_nt != vt) {  // first tile of the kernel
                         const int v0 = vt * kTileN + grp * kGrpCols + gtid;
@@ -560,17 +566,41 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                     const int v0 = nb_nt * kTileN + grp * kGrpCols + gtid;
                     nb0 = v0 < p.V ? __ldg(p.bias + v0) : 0.f;
                 }
+#ifdef TSASR_EPI_PROF
+                if (p.prof) { const long long c = clock64(); pe_bar += c - pe_t; pe_t = c; }
+#endif
                 mbar_wait(&acc_full[buf], acc_phase, 0x600 | buf);
+#ifdef TSASR_EPI_PROF
+                if (p.prof) { const long long c = clock64(); pe_wait += c - pe_t; pe_t = c; }
+#endif
                 tcgen05_fence_after();
                 const int n_all = vt == NT - 1 ? p.n_last : kTileN;
                 const int c_begin = grp * kGrpCols, n_cols = min(n_all, c_begin + kGrpCols);  // this group's columns [c_begin, n_cols)
+                // chunks (16 columns each) of this group's half tile that need the rare path of process(): bit i <-> cc = c_begin + 16 i
+                uint32_t special_mask = 0;
+                uint8_t* img_grp = nullptr;  // MODE_GRAD: first dY image of this group's half tile
+                if (MODE == MODE_GRAD)
+                    img_grp = reinterpret_cast<uint8_t*>(p.dY_img) + ((size_t)(tile - p.tile_begin) * (NT * 4) + vt * 4 + grp * 2) * kABlockBytes;
+                if (MODE == MODE_FWD || MODE == MODE_GRAD) {
+                    const int g0 = vt * kTileN + c_begin;  // first vocabulary column of this group's half tile
+                    if ((unsigned)(p.blank - g0) < (unsigned)kGrpCols) special_mask |= 1u << ((p.blank - g0) >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < n_lab && (unsigned)(lab_w[k] - g0) < (unsigned)kGrpCols) special_mask |= 1u << ((lab_w[k] - g0) >> 4);
+                    if (g0 + kGrpCols > p.V) {  // the vocabulary ends inside (or before) this half tile
+                        const int first = max(0, (p.V - g0) >> 4);  // first chunk with col0 + 16 > V
+                        special_mask |= first < 8 ? (0xffu << first) & 0xffu : 0u;
+                    }
+                }
                 // TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c is processed
                 uint32_t raw0[16], raw1[16];
-                auto process = [&](const uint32_t (&raw)[16], const int cc) {
+                auto process = [&](const uint32_t (&raw)[16], const int ci) {  // ci: chunk of 16 columns inside the group's half tile (0..7)
+                    const int cc = c_begin + 16 * ci;
                     const int col0 = vt * kTileN + cc;
+                    const bool special = (special_mask >> ci) & 1u;
                     // y = logit * log2(e) = acc * log2(e) + bias * log2(e), two columns per instruction
                     float2 y2[8];
-                    const float4* b4 = reinterpret_cast<const float4*>(bias_g + (cc - c_begin));
+                    const float4* b4 = reinterpret_cast<const float4*>(bias_g + 16 * ci);
                     const float2 l2e = make_float2(kLog2eF, kLog2eF);
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
@@ -582,10 +612,34 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                     }
                     float* y = reinterpret_cast<float*>(y2);
                     if (MODE == MODE_FWD) {
-                        if (col0 + 16 > p.V) {
+                        // Rare work first, behind ONE warp-uniform branch per chunk (special: this chunk holds the blank
+                        // column, one of the warp's label columns, or the end of the vocabulary).  Measured: with the
+                        // range checks inline (5 not-taken branches per chunk) the epilogue needed 8.5k cycles per
+                        // vocabulary tile against 5.1k for the MMAs and paced the whole kernel.
+                        if (special) {
+                            // blank / label logits: the column index is warp-uniform per label position
+                            if (p.blank >= col0 && p.blank < col0 + 16) {
+                                const int idx = p.blank - col0;
 #pragma unroll
-                            for (int jj = 0; jj < 16; ++jj)
-                                if (col0 + jj >= p.V) y[jj] = -INFINITY;
+                                for (int jj = 0; jj < 16; ++jj)
+                                    if (jj == idx) y_blank = y[jj];
+                            }
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (k < n_lab && lab_w[k] >= col0 && lab_w[k] < col0 + 16) {
+                                    const int idx = lab_w[k] - col0;
+                                    float sel = 0.f;
+#pragma unroll
+                                    for (int jj = 0; jj < 16; ++jj)
+                                        if (jj == idx) sel = y[jj];
+                                    if ((lane >> p.tT_log2) == k || n_lab == 1) y_label = sel;
+                                }
+                            }
+                            if (col0 + 16 > p.V) {
+#pragma unroll
+                                for (int jj = 0; jj < 16; ++jj)
+                                    if (col0 + jj >= p.V) y[jj] = -INFINITY;
+                            }
                         }
                         // pairwise trees keep the dependency chains short
                         float m8[8], m4[4];
@@ -607,24 +661,6 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                         const float2 s2 = fadd2(s4a, s4b);
                         run_s = fmaf(run_s, ex2_approx(run_m - mn), s2.x + s2.y);
                         run_m = mn;
-                        // blank / label logits: the column index is warp-uniform per label position
-                        if (p.blank >= col0 && p.blank < col0 + 16) {
-                            const int idx = p.blank - col0;
-#pragma unroll
-                            for (int jj = 0; jj < 16; ++jj)
-                                if (jj == idx) y_blank = y[jj];
-                        }
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (k < n_lab && lab_w[k] >= col0 && lab_w[k] < col0 + 16) {
-                                const int idx = lab_w[k] - col0;
-                                float sel = 0.f;
-#pragma unroll
-                                for (int jj = 0; jj < 16; ++jj)
-                                    if (jj == idx) sel = y[jj];
-                                if ((lane >> p.tT_log2) == k || n_lab == 1) y_label = sel;
-                            }
-                        }
                     } else if (MODE == MODE_GRAD) {
                         // dlogits = occ * softmax - [blank] ob - [label] oe, emitted as bf16 into the
                         // [128 x 64] SWIZZLE_128B image of this (tile, 64-column block)
@@ -633,28 +669,29 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj) {
                             const float2 d = fadd2(y2[jj], nz);
-                            float2 g = fmul2(make_float2(ex2_approx(d.x), ex2_approx(d.y)), oc);
-                            if (col0 + 16 > p.V) {
-                                if (col0 + 2 * jj >= p.V) g.x = 0.f;
-                                if (col0 + 2 * jj + 1 >= p.V) g.y = 0.f;
-                            }
+                            const float2 g = fmul2(make_float2(ex2_approx(d.x), ex2_approx(d.y)), oc);
                             packed[jj] = pack_bf16x2(g.x, g.y);
                         }
-                        const int vb = col0 >> 6;             // 64-column block index
-                        const int chunk0 = (col0 & 63) >> 3;  // 0, 2, 4 or 6
-                        uint8_t* img = reinterpret_cast<uint8_t*>(p.dY_img) +
-                                       ((size_t)(tile - p.tile_begin) * (NT * 4) + vb) * kABlockBytes;
-                        // the two 16-byte chunks of these 16 columns share one 32-byte sector of the swizzled row
-                        // (chunk0 is even, the XOR with row & 7 only swaps them for odd rows): ONE 256-bit store
+                        if (special && col0 + 16 > p.V) {  // end of the vocabulary: padded columns are exact zeros
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) {
+                                if (col0 + 2 * jj >= p.V) packed[jj] &= 0xffff0000u;
+                                if (col0 + 2 * jj + 1 >= p.V) packed[jj] &= 0x0000ffffu;
+                            }
+                        }
+                        // image of this (tile, 64-column block): vb = col0 >> 6 = 4 vt + 2 grp + (ci >> 2); the two
+                        // 16-byte chunks of these 16 columns share one 32-byte sector of the swizzled row (their chunk
+                        // index (ci & 3) * 2 is even, the XOR with row & 7 only swaps them for odd rows): ONE 256-bit store
+                        uint8_t* img = img_grp + (size_t)(ci >> 2) * kABlockBytes;
                         {
                             const bool swap = row & 1;
-                            uint8_t* dst = img + (uint32_t)row * 128u + ((((uint32_t)chunk0 ^ ((uint32_t)row & 7u)) >> 1) << 5);
+                            uint8_t* dst = img + (uint32_t)row * 128u + ((((uint32_t)(ci & 3)) ^ (((uint32_t)row & 7u) >> 1)) << 5);
                             st_global_v8(dst, swap ? packed[4] : packed[0], swap ? packed[5] : packed[1], swap ? packed[6] : packed[2],
                                          swap ? packed[7] : packed[3], swap ? packed[0] : packed[4], swap ? packed[1] : packed[5],
                                          swap ? packed[2] : packed[6], swap ? packed[3] : packed[7]);
                         }
                         // patch the two special columns from the saved lattice (same thread, program order)
-                        if (valid) {
+                        if (special && valid) {
                             __nv_bfloat16* rowp = reinterpret_cast<__nv_bfloat16*>(img);
                             if (p.blank >= col0 && p.blank < col0 + 16) {
                                 float g = occ * p_blank - ob;
@@ -677,16 +714,23 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                         }
                     }
                 };
-                if (c_begin < n_cols) tmem_ld_32x32b_x16(tmem_row + c_begin, raw0);
-                for (int cc = c_begin; cc < n_cols; cc += 32) {
-                    tmem_ld_wait();
+                const bool abl_nomath = p.dbg_skip & 8, abl_nold = p.dbg_skip & 16;  // development ablations
+                if (abl_nold) {
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) { raw0[jj] = 0x3f800000u + jj; raw1[jj] = 0x3f900000u + jj; }
+                }
+                if (c_begin < n_cols && !abl_nold) tmem_ld_32x32b_x16(tmem_row + c_begin, raw0);
+                for (int ci = 0; ci < kGrpCols / 16; ci += 2) {  // two chunks of 16 columns per iteration (code size: the
+                    const int cc = c_begin + 16 * ci;            // unrolled form was slower, instruction fetch)
+                    if (cc >= n_cols) break;
+                    if (!abl_nold) tmem_ld_wait();
                     const bool more1 = cc + 16 < n_cols;
-                    if (more1) tmem_ld_32x32b_x16(tmem_row + cc + 16, raw1);
-                    process(raw0, cc);
+                    if (more1 && !abl_nold) tmem_ld_32x32b_x16(tmem_row + cc + 16, raw1);
+                    if (!abl_nomath) process(raw0, ci);
                     if (more1) {
-                        tmem_ld_wait();
-                        if (cc + 32 < n_cols) tmem_ld_32x32b_x16(tmem_row + cc + 32, raw0);
-                        process(raw1, cc + 16);
+                        if (!abl_nold) tmem_ld_wait();
+                        if (cc + 32 < n_cols && !abl_nold) tmem_ld_32x32b_x16(tmem_row + cc + 32, raw0);
+                        if (!abl_nomath) process(raw1, ci + 1);
                     }
                 }
                 if (MODE == MODE_GRAD && n_all < kTileN) {
@@ -707,6 +751,9 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_release[buf]);
+#ifdef TSASR_EPI_PROF
+                if (p.prof) pe_proc += clock64() - pe_t;
+#endif
             }
             if (MODE == MODE_FWD) {
                 // merge the two groups' running (max, sum) and picked logits; group 0 writes the lattice
@@ -727,6 +774,12 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
             }
             ++it;
         }
+#ifdef TSASR_EPI_PROF
+        if (p.prof && (warp_idx & 3) == 0 && lane == 0) {
+            long long* o = p.prof + blockIdx.x * 16 + 8 + grp * 4;
+            o[0] = pe_wait; o[1] = pe_proc; o[2] = pe_bar; o[3] = acc_it;
+        }
+#endif
     }
 
     tcgen05_fence_before();
