@@ -23,10 +23,11 @@
 //                softmax and emit bf16 dlogits tiles as pre-swizzled operand images for the backward
 //                GEMMs; MODE_DEBUG: dump raw logits (tests only).
 //
-// Measured ceiling (TSASR_DEBUG_SKIP ablations, B200, config 2): with epilogue, producers and W stream all
-// disabled a pair round takes 22.7k cycles (20.5k = 160 MMAs x 128); each of the three adds 3.5-5k cycles on
-// its own and the sum is ~additive (36k).  K = H = 640 means an accumulator is drained from TMEM every 10
-// pipeline stages, and TMEM drains, operand writes and the MMA's own operand reads contend inside the SM.
+// What paces the kernel (TSASR_DEBUG_SKIP ablations + epilogue cycle counters, B200, config 2,
+// profiles/r1_ablation_joint_epilogue.txt): a pair round is 20.5k cycles of MMAs, but with the MMA issue switched OFF the
+// round still takes 32.5k cycles -- the epilogue needs ~6k cycles per accumulator (two in-order warps per SM
+// sub-partition cannot hide the scale -> max tree -> exp2 -> sum chain) against 5.1k for the MMAs that fill it.  The
+// rare per-chunk work (blank / label picks, vocabulary tail) therefore sits behind ONE warp-uniform branch per chunk.
 //
 // PAIR = true runs the same roles on CTA pairs (2-CTA clusters, tcgen05 cta_group::2): the pair works on two
 // cell tiles at once with ONE M=256 MMA stream issued by the leader CTA; each CTA keeps its own A operand,
@@ -86,7 +87,8 @@ struct JointParams {
     int NT;                     // ceil(V / 256)
     int n_last;                 // UMMA N of the last vocabulary tile (multiple of 16)
     int num_w_stages;
-    int dbg_skip;               // development ablations: 1 = epilogue only releases, 2 = producers only arrive, 4 = no W stream
+    int dbg_skip;               // development ablations (bits): 1 epilogue only releases, 2 producers only arrive, 4 no W stream,
+                                // 8 epilogue loads but no math, 16 epilogue math but no TMEM loads, 32 MMA issue skipped
     const __nv_bfloat16* enc;   // [B,T,H]
     const __nv_bfloat16* dec;   // [B,U,H]
     // MODE_FWD outputs (skewed lattice layout)
