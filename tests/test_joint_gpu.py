@@ -353,6 +353,25 @@ def test_backward_tile_pruning_is_invisible_in_fp32():
         assert _rel_err(c, a) < 1e-5
 
 
+@pytest.mark.parametrize("V,blank", [(300, -1), (300, 137), (1000, 255), (1000, 256), (1000, 999), (40, 16), (257, 256)])
+def test_fused_path_blank_anywhere_in_the_vocabulary(V, blank):
+    """The blank column may sit in any 16-column chunk of any vocabulary tile (torchaudio's default is -1 = V-1): the
+    epilogue finds it through the per-tile special-chunk mask.  Against the CPU reference chain (torchaudio rnnt_loss)."""
+    B, T, U, H = 3, 21, 12, 128
+    enc, dec, W, b, targets, ll, tl = _inputs(B, T, U, H, V, seed=7 * V + blank)
+    bl = blank % V
+    targets = torch.where(targets == bl, torch.full_like(targets, (bl + 1) % V), targets)  # labels never equal the blank
+    d = _dev()
+    e, dc, w, bb = (x.to(d).float().requires_grad_() for x in (enc, dec, W, b))
+    costs = tsasr_b200.fused_joint_rnnt_loss(e, dc, w, bb, targets.to(d), ll.to(d), tl.to(d), blank=blank, reduction="none")
+    dcost = torch.linspace(0.5, 1.5, B)
+    (costs * dcost.to(d)).sum().backward()
+    ref = reference_joint_loss_fwd_bwd(enc, dec, W, b, targets, ll, tl, bl, "leaky_relu", 0.01, round_bf16=True, dcost=dcost)
+    np.testing.assert_allclose(costs.detach().cpu().numpy(), ref["costs"].numpy(), rtol=LOSS_RTOL)
+    for got, key in ((e.grad, "d_enc"), (dc.grad, "d_dec"), (w.grad, "dW"), (bb.grad, "db")):
+        assert _rel_err(got.cpu(), ref[key]) < GRAD_REL, key
+
+
 def test_fused_path_fuzz_vs_compat_path():
     """Random shapes, ragged lengths, activations, chunk sizes: the fused tcgen05 path (tile pruning on) against the
     compat kernels (materialised logits built by torch from the same bf16-rounded operands; themselves pinned on the
