@@ -231,13 +231,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must never hang the GPU (a hung box is a strike).  After
-// ~2^27 failed probes (seconds) the CTA records the barrier id and traps.
+// Bounded wait: a protocol bug must never hang the GPU (a hung box is a strike).  A failed try_wait probe returns after
+// a hardware suspend of a few microseconds (measured: 2^27 probes took ~9 minutes), so 2^21 probes bound a wait to a few
+// seconds -- orders of magnitude beyond any legitimate wait of these kernels; then the CTA records the barrier id and traps.
 static __device__ unsigned int g_tsasr_hang_info[4];
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 27)) {
+        if (++spins > (1u << 21)) {
             g_tsasr_hang_info[0] = 0xDEAD0000u | tag;
             g_tsasr_hang_info[1] = blockIdx.x;
             g_tsasr_hang_info[2] = threadIdx.x;
