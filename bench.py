@@ -163,6 +163,30 @@ def cpu_reference_step(sample, threads):
     return sample["B"] * sample["T"] * sample["U"] / best, best
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_reference_single_thread(sample):
+    """Same chain on ONE host thread (SURVEY 8d asks for both): one untimed warm-up on all threads has already run,
+    so a single timed step bounds the extra cost to a few seconds."""
+    from oracle.reference_chain import reference_joint_loss_fwd_bwd
+
+    enc, dec, W, b, targets, ll, tl = synth(sample, "cpu", seed=1)
+    torch.set_num_threads(1)
+    t0 = time.perf_counter()
+    reference_joint_loss_fwd_bwd(enc, dec, W, b, targets, ll, tl, 0, "leaky_relu", 0.01, round_bf16=False, reduction="mean")
+    dt = time.perf_counter() - t0
+    return sample["B"] * sample["T"] * sample["U"] / dt, dt
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -190,7 +214,8 @@ def run_reference(args, rank):
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(), "cpu_sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample_txt},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample_txt,
+                         "cpu_model": cpu_model()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -489,7 +514,11 @@ def main():
                 "value": v, "unit": UNIT, "cores": threads, "kind": "reference",
                 "sample": ("torch eager joint+Linear + torchaudio.functional.rnnt_loss CPU + backward (the reference's CPU path, "
                            f"oracle/reference_chain.py) on B={CPU_SAMPLE['B']},T={CPU_SAMPLE['T']},U={CPU_SAMPLE['U']},V={CPU_SAMPLE['V']},"
-                           f"H={CPU_SAMPLE['H']} fp32, 1 warm-up + best of 3 ({secs:.2f} s/step)")}
+                           f"H={CPU_SAMPLE['H']} fp32, 1 warm-up + best of 3 ({secs:.2f} s/step)"),
+                "cpu_model": cpu_model()}
+            v1, secs1 = cpu_reference_single_thread(CPU_SAMPLE)
+            torch.set_num_threads(threads)
+            out["cpu_baseline"]["single_thread"] = {"value": v1, "unit": UNIT, "cores": 1, "s_per_step": secs1}
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()

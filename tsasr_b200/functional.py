@@ -4,6 +4,8 @@
 vendor/speechbrain/speechbrain/nnet/losses.py:72-79 -- in signature, semantics and error behaviour
 (same exception types for the same precondition violations).
 """
+import threading
+
 import torch
 
 from . import _lib, ops
@@ -47,15 +49,14 @@ class _DeferredLengthCheck:
     so an invalid input cannot index out of bounds before ``finish`` raises (same exception types and messages
     as ``_validate_lengths``)."""
 
-    _side, _pinned = {}, {}
+    _tls = threading.local()  # side stream + pinned landing buffer per (thread, device): calls from two threads never share one
 
     def __init__(self, stats, ready):
         dev = stats.device
-        side = self._side.get(dev)
-        if side is None:
-            side = self._side[dev] = torch.cuda.Stream(dev)
-            self._pinned[dev] = torch.empty((4,), dtype=torch.int32).pin_memory()
-        self.host = self._pinned[dev]
+        cache = self._tls.__dict__.setdefault("cache", {})
+        if dev not in cache:
+            cache[dev] = (torch.cuda.Stream(dev), torch.empty((4,), dtype=torch.int32).pin_memory())
+        side, self.host = cache[dev]
         side.wait_event(ready)
         with torch.cuda.stream(side):
             self.host.copy_(stats, non_blocking=True)

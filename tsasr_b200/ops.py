@@ -125,13 +125,15 @@ _workspaces = {}
 
 
 def _workspace(dev, nbytes):
-    """Per-device cached workspace (grown on demand; torch caching allocator owns the memory)."""
-    ws = _workspaces.get(dev)
+    """Cached workspace per (device, stream) -- two backward passes queued on different streams of one device must not
+    share their operand images -- grown on demand; the torch caching allocator owns the memory."""
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = None
-        _workspaces[dev] = None
+        _workspaces[key] = None
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-        _workspaces[dev] = ws
+        _workspaces[key] = ws
     return ws
 
 
