@@ -164,7 +164,7 @@ def test_fused_dlogits_images_vs_oracle():
                                              reduction="none", max_chunk_cells=1 << 30, prune_log2_eps=0.0)  # every tile written
     costs.sum().backward()
     torch.cuda.synchronize()
-    got = _decode_dy_images(ops._workspaces[d], B, T, U, V).numpy()
+    got = _decode_dy_images(ops.last_workspace(d), B, T, U, V).numpy()
     _, logits = rn.joint_logits(enc.float().numpy(), dec.float().numpy(), W.float().numpy(), b.numpy(), "leaky_relu")
     _, want = rn.rnnt_torchaudio(logits, targets.numpy(), ll.numpy(), tl.numpy(), 0)
     for bi in range(B):  # tiles entirely outside the T_b x U_b rectangle are never written (nor read)

@@ -137,6 +137,11 @@ def _workspace(dev, nbytes):
     return ws
 
 
+def last_workspace(dev):
+    """The workspace the last joint_bwd on ``dev`` used (test / debugging helper: its head holds the operand images)."""
+    return _last_bwd[dev][0]
+
+
 def default_prune_log2_eps():
     """Backward tile pruning threshold (log2 of the smallest alignment posterior a tile must reach to be kept);
     TSASR_PRUNE_LOG2_EPS overrides the default -30, any value >= 0 switches pruning off."""
