@@ -96,3 +96,23 @@ def test_relative_length_conversion_bit_exact(golden):
     g = golden("half_rounding_torchaudio")
     rel = torch.tensor(g["input_rel"])
     assert torch.equal((rel * 8).round().int(), torch.tensor(g["input_abs"]))
+
+
+@pytest.mark.parametrize("reduction", ["mean", "sum", "none"])
+def test_numba_branch_reduction_node_matches_the_reference_scaling(reduction):
+    """``_NumbaReduce`` (the value / gradient scale of the reference's Numba branch on top of the fused per-utterance
+    costs): value reduce_b(cost_b / T_b) (SB/nnet/loss/transducer_loss.py:104-106,280-287), gradient w.r.t. cost_b =
+    grad_output broadcast -- the reduction and the division are NOT differentiated (:289-293)."""
+    from tsasr_b200.functional import _NumbaReduce
+
+    costs = torch.tensor([10.0, 20.0, 36.0], requires_grad=True)
+    T = torch.tensor([5, 4, 9], dtype=torch.int32)
+    out = _NumbaReduce.apply(costs, T, reduction)
+    per_utt = torch.tensor([2.0, 5.0, 4.0])
+    want = {"mean": per_utt.mean(), "sum": per_utt.sum(), "none": per_utt}[reduction]
+    assert torch.allclose(out, want)
+    gout = torch.tensor([1.0, 2.0, 3.0]) if reduction == "none" else torch.tensor(0.5)
+    out.backward(gout)
+    assert torch.equal(costs.grad, gout.expand(3))
+    with pytest.raises(Exception, match="Unexpected reduction"):
+        _NumbaReduce.apply(costs, T, "max")
