@@ -132,7 +132,10 @@ def _decode_dy_images(ws, B, T, U, V):
 
 @pytest.mark.parametrize("shape,act", [((2, 24, 9, 64, 40), "leaky_relu"), ((2, 16, 6, 64, 33), "tanh"),
                                        ((2, 40, 17, 640, 1000), "leaky_relu"), ((2, 30, 40, 320, 29), "relu"),
-                                       ((3, 20, 1, 128, 50), "leaky_relu"), ((1, 9, 130, 384, 257), "leaky_relu")])
+                                       ((3, 20, 1, 128, 50), "leaky_relu"), ((1, 9, 130, 384, 257), "leaky_relu"),
+                                       # H not a multiple of 64: zero-padded to whole k-blocks by the fused op
+                                       ((2, 18, 7, 100, 90), "tanh"), ((2, 12, 5, 40, 30), "leaky_relu"),
+                                       ((1, 20, 9, 600, 300), "relu")])
 def test_fused_backward_vs_reference_chain(shape, act):
     B, T, U, H, V = shape
     enc, dec, W, b, targets, ll, tl = _inputs(B, T, U, H, V, seed=sum(shape) + 2)

@@ -221,7 +221,12 @@ class FusedJointRnnt(torch.autograd.Function):
     @staticmethod
     def forward(ctx, enc, dec, W, bias, targets, logit_lengths, target_lengths, blank, act_kind, act_param,
                 max_chunk_cells, prune_log2_eps=None):
-        enc16, dec16, W16 = _operands_bf16(enc.detach(), dec.detach(), W.detach())
+        H = enc.shape[-1]
+        enc_, dec_, W_ = enc.detach(), dec.detach(), W.detach()
+        if H % 64:  # the kernels contract over whole 64-wide k-blocks: zero columns add nothing (act(0) = 0 for every
+            pad = (0, 64 - H % 64)  # fused activation, and the padded W columns are zero anyway)
+            enc_, dec_, W_ = (torch.nn.functional.pad(t, pad) for t in (enc_, dec_, W_))
+        enc16, dec16, W16 = _operands_bf16(enc_, dec_, W_)
         b32 = bias.detach().to(torch.float32).contiguous()
         B, T, _ = enc16.shape
         U = dec16.shape[1]
@@ -230,6 +235,7 @@ class FusedJointRnnt(torch.autograd.Function):
         ctx.save_for_backward(enc16, dec16, W16, b32, targets, logit_lengths, target_lengths, lat2, logz, alpha, beta, cost)
         ctx.cfg = (blank, act_kind, act_param, max_chunk_cells, prune_log2_eps)
         ctx.in_dtypes = (enc.dtype, dec.dtype, W.dtype, bias.dtype)
+        ctx.H = H
         return cost
 
     @staticmethod
@@ -240,6 +246,8 @@ class FusedJointRnnt(torch.autograd.Function):
         d_enc, d_dec, dW, db = ops.joint_bwd(enc16, dec16, W16, b32, targets, ll, tl, blank, act_kind, act_param,
                                              lat2, logz, alpha, beta, cost, dcost, max_chunk_cells, prune_log2_eps)
         de, dd, dw, dbt = ctx.in_dtypes
+        if d_enc.shape[-1] != ctx.H:  # drop the gradients of the zero padding
+            d_enc, d_dec, dW = d_enc[..., :ctx.H].contiguous(), d_dec[..., :ctx.H].contiguous(), dW[:, :ctx.H].contiguous()
         return (d_enc.to(de), d_dec.to(dd), dW.to(dw), db.to(dbt), None, None, None, None, None, None, None, None)
 
 
