@@ -167,8 +167,8 @@ __host__ __device__ inline SmemLayout smem_layout(int KB, int num_w_stages) {
     l.a_off = 0;
     l.w_off = l.a_off + (uint32_t)KB * kABlockBytes;
     l.bias_off = l.w_off + (uint32_t)num_w_stages * kWStageBytes;
-    l.xchg_off = l.bias_off + 2 * kTileN * 4;
-    l.bar_off = l.xchg_off + 2 * kTileM * 16;
+    l.xchg_off = l.bias_off + 2 * (kTileN / 2) * 4;  // one 128-float bias slot per epilogue group
+    l.bar_off = l.xchg_off + kTileM * 8;              // 128 x float2, used twice per cell tile (MODE_FWD merge)
     // barriers: w_full[4] w_empty[4] (4 spare) a_full[10] a_empty[10] acc_full[2] acc_empty[2] = 36,
     // a_done[10] acc_done[2] (partner CTA only: local collection points relayed to the leader) = 48
     l.tmem_off = l.bar_off + 48 * 8;
@@ -289,7 +289,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
     uint8_t* smem_a = smem + L.a_off;
     uint8_t* smem_w = smem + L.w_off;
     float* bias_s = reinterpret_cast<float*>(smem + L.bias_off);
-    float4* xchg = reinterpret_cast<float4*>(smem + L.xchg_off);
+    float2* xchg = reinterpret_cast<float2*>(smem + L.xchg_off);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
     uint64_t* w_full = bars;
     uint64_t* w_empty = bars + 4;
@@ -394,6 +394,29 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                     const uint32_t idesc = nt == NT - 1 ? idesc_last : idesc_full;
                     const bool first_nt = nt == 0, last_nt = nt == NT - 1;
                     uint32_t a_lo = a_lo0;
+                    if (PAIR && NS == 4 && !(KB & 1) && !(p.dbg_skip & 256)) {
+                        // Two k-blocks (8 MMAs) per wait / commit group: measured 5 % faster than one group per k-block (the
+                        // per-stage wait -> 4 MMAs -> commit structure, not the W bytes, is what the W stream costs; bit 256 of
+                        // TSASR_DEBUG_SKIP selects the per-stage loop for A/B runs)
+                        for (int kb = 0; kb < KB; kb += 2, a_lo += 2 * (kABlockBytes >> 4)) {
+                            if (first_nt) {
+                                mbar_wait(&a_full[kb], it & 1, 0x300 | kb);
+                                mbar_wait(&a_full[kb + 1], it & 1, 0x300 | (kb + 1));
+                            }
+                            mbar_wait(&w_full[stage], phase, 0x400 | stage);
+                            mbar_wait(&w_full[stage + 1], phase, 0x400 | (stage + 1));
+                            tcgen05_fence_after();
+                            const uint32_t w_lo = w_lo0 + stage * (kWStageBytes >> 4);
+                            umma_bf16_2cta_x4_e(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)w_hi << 32) | w_lo, idesc, kb != 0);
+                            umma_bf16_2cta_x4_e(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + (kABlockBytes >> 4)),
+                                                ((uint64_t)w_hi << 32) | (w_lo + (kWStageBytes >> 4)), idesc, true);
+                            umma_commit_2cta_e(&w_empty[stage], 1);
+                            umma_commit_2cta_e(&w_empty[stage + 1], 1);
+                            stage += 2;
+                            if (stage == 4u) { stage = 0; phase ^= 1; }
+                            if (last_nt) { umma_commit_2cta_e(&a_empty[kb], 3); umma_commit_2cta_e(&a_empty[kb + 1], 3); }
+                        }
+                    } else
                     for (int kb = 0; kb < KB; ++kb, a_lo += kABlockBytes >> 4) {
                         if (first_nt) {
                             if (p.prof) tm = clock64();
@@ -488,7 +511,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
         const int tTm = (1 << p.tT_log2) - 1;
         const int n_lab = max(1, 32 >> p.tT_log2);  // distinct label positions inside one warp
         const uint32_t tmem_row0 = tmem_base + ((uint32_t)(q * 32) << 16);
-        float* bias_g = bias_s + grp * kTileN;  // this group's 128 staged bias values (second half of the slot unused)
+        float* bias_g = bias_s + grp * (kTileN / 2);  // this group's 128 staged bias values
         constexpr int kGrpCols = kTileN / 2;
         uint32_t acc_it = 0, it = 0;
 #ifdef TSASR_EPI_PROF
@@ -511,7 +534,10 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_release[buf]);
                 }
-                if (MODE == MODE_FWD) asm volatile("bar.sync 3, 256;" ::: "memory");
+                if (MODE == MODE_FWD) {  // the merge of a cell tile passes four barriers
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) asm volatile("bar.sync 3, 256;" ::: "memory");
+                }
                 ++it;
                 continue;
             }
@@ -758,16 +784,23 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
 #endif
             }
             if (MODE == MODE_FWD) {
-                // merge the two groups' running (max, sum) and picked logits; group 0 writes the lattice
-                float4* xb = xchg + (it & 1) * kTileM;
-                if (grp == 1) xb[row] = make_float4(run_m, run_s, y_blank, y_label);
+                // merge the two groups' running (max, sum) and picked logits; group 0 writes the lattice.  The exchange
+                // buffer is one float2 per row and is used twice ((max, sum), then the picked logits): the shared memory
+                // saved buys the fourth W stage at H = 640.  Barriers: buffer free / (max, sum) written / read / picks written.
+                asm volatile("bar.sync 3, 256;" ::: "memory");
+                if (grp == 1) xchg[row] = make_float2(run_m, run_s);
+                asm volatile("bar.sync 3, 256;" ::: "memory");
+                float2 o_ms = make_float2(-INFINITY, 0.f);
+                if (grp == 0) o_ms = xchg[row];
+                asm volatile("bar.sync 3, 256;" ::: "memory");
+                if (grp == 1) xchg[row] = make_float2(y_blank, y_label);
                 asm volatile("bar.sync 3, 256;" ::: "memory");
                 if (grp == 0 && valid) {
-                    const float4 o = xb[row];
-                    const float mn = fmaxf(run_m, o.x);
-                    const float s = run_s * ex2_approx(run_m - mn) + o.y * ex2_approx(o.x - mn);
+                    const float2 o_y = xchg[row];
+                    const float mn = fmaxf(run_m, o_ms.x);
+                    const float s = run_s * ex2_approx(run_m - mn) + o_ms.y * ex2_approx(o_ms.x - mn);
                     const float lz2 = mn + lg2_approx(s);
-                    const float yb = fmaxf(y_blank, o.z), yl = fmaxf(y_label, o.w);
+                    const float yb = fmaxf(y_blank, o_y.x), yl = fmaxf(y_label, o_y.y);
                     const float lpb = (yb - lz2) * kLn2F;
                     const float lpe = label >= 0 ? (yl - lz2) * kLn2F : -INFINITY;
                     p.lat2[cell_o] = make_float2(lpb, lpe);
