@@ -92,7 +92,8 @@ int tsasr_logprobs_grad(const int32_t* targets, const int32_t* logit_lengths, co
  * loss, as chained at train_librispeechmix_scratch.py:132,135,158.
  *   enc  bf16 [B,T,H]   dec bf16 [B,U,H]   W bf16 [V,H]   bias fp32 [V]
  *   out: lat2 (float2 per cell), logz (log-sum-exp per cell), skewed layout.
- * Requirements: H % 64 == 0, 64 <= H <= 640, V >= 2.  tcgen05 / TMEM / TMA kernel. */
+ * Requirements: H % 64 == 0, 64 <= H <= 640, V >= 2 (a host that has another H <= 640 zero-pads enc, dec and W to the next
+ * multiple of 64, which is exact; tsasr_b200/functional.py does).  tcgen05 / TMEM / TMA kernel. */
 int tsasr_joint_fwd(const void* enc, const void* dec, const void* W, const float* bias, const int32_t* targets,
                     const int32_t* logit_lengths, const int32_t* target_lengths, int B, int T, int U, int H, int V,
                     int blank, int act_kind, float act_param, float* lat2, float* logz, tsasr_stream_t stream);
