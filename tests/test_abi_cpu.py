@@ -116,3 +116,26 @@ def test_numba_branch_reduction_node_matches_the_reference_scaling(reduction):
     assert torch.equal(costs.grad, gout.expand(3))
     with pytest.raises(Exception, match="Unexpected reduction"):
         _NumbaReduce.apply(costs, T, "max")
+
+
+def test_install_into_speechbrain_patches_the_three_import_names(monkeypatch):
+    """``install_into_speechbrain`` swaps exactly the names the recipe's yaml resolves (conformer-t_scratch.yaml:191-193,
+    262-264 -> speechbrain.nnet.transducer.transducer_joint.Transducer_joint, speechbrain.nnet.losses.transducer_loss)
+    plus the Numba-branch classes; checked on stub modules (speechbrain itself is not importable on the test box)."""
+    import sys
+    import types
+
+    names = ["speechbrain", "speechbrain.nnet", "speechbrain.nnet.losses", "speechbrain.nnet.transducer",
+             "speechbrain.nnet.transducer.transducer_joint", "speechbrain.nnet.loss", "speechbrain.nnet.loss.transducer_loss"]
+    mods = {n: types.ModuleType(n) for n in names}
+    for n, m in mods.items():
+        monkeypatch.setitem(sys.modules, n, m)
+        if "." in n:
+            setattr(mods[n.rsplit(".", 1)[0]], n.rsplit(".", 1)[1], m)
+    mods["speechbrain.nnet.losses"].transducer_loss = object()
+    mods["speechbrain.nnet.transducer.transducer_joint"].Transducer_joint = object()
+    tsasr_b200.install_into_speechbrain()
+    assert mods["speechbrain.nnet.losses"].transducer_loss is tsasr_b200.transducer_loss
+    assert mods["speechbrain.nnet.transducer.transducer_joint"].Transducer_joint is tsasr_b200.Transducer_joint
+    assert mods["speechbrain.nnet.loss.transducer_loss"].TransducerLoss is tsasr_b200.TransducerLoss
+    assert mods["speechbrain.nnet.loss.transducer_loss"].Transducer is tsasr_b200.Transducer
