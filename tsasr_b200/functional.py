@@ -202,7 +202,10 @@ def _operands_bf16(enc, dec, W):
     """bf16 copies of the three GEMM operands: one launch when all are contiguous fp32 (the recipe's case)."""
     ts = (enc, dec, W)
     if all(t.dtype == torch.float32 and t.is_contiguous() and t.numel() % 4 == 0 and t.data_ptr() % 16 == 0 for t in ts):
-        outs = tuple(torch.empty(t.shape, dtype=torch.bfloat16, device=t.device) for t in ts)
+        # one allocation for the three copies: H % 64 == 0 here (FusedJointRnnt pads), so every slice starts 128-byte aligned
+        n0, n1, n2 = (t.numel() for t in ts)
+        buf = torch.empty((n0 + n1 + n2,), dtype=torch.bfloat16, device=enc.device)
+        outs = (buf[:n0].view(enc.shape), buf[n0: n0 + n1].view(dec.shape), buf[n0 + n1:].view(W.shape))
         _lib.check(_lib.load().tsasr_cast_operands_bf16(
             enc.data_ptr(), enc.numel(), dec.data_ptr(), dec.numel(), W.data_ptr(), W.numel(),
             outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), torch.cuda.current_stream(enc.device).cuda_stream))

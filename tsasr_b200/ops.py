@@ -14,11 +14,13 @@ _DTYPE_CODE = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16:
 
 
 def _p(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    # plain integers: the argtypes in _lib.SIGNATURES convert them (a ctypes object per pointer costs ~0.5 us, and the
+    # host time in front of the first kernel of a step is GPU idle time)
+    return t.data_ptr() if t is not None else None
 
 
 def _stream(device):
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 class _on_device:
