@@ -51,19 +51,33 @@ def reference_joint_logits(enc, dec, W, bias, act="leaky_relu", act_param=0.01, 
 
 def reference_joint_loss_fwd_bwd(enc, dec, W, bias, targets, logit_lengths, target_lengths, blank=0,
                                  act="leaky_relu", act_param=0.01, round_bf16=False, reduction="none",
-                                 dcost=None, num_threads=None):
-    """Full CPU chain joint -> head -> rnnt_loss -> backward; returns dict of fp32 tensors."""
+                                 dcost=None, num_threads=None, keep_intermediates=False):
+    """Full CPU chain joint -> head -> rnnt_loss -> backward; returns dict of fp32 tensors.
+    ``keep_intermediates`` adds "dlogits" [B,T,U,V] (the gradient the reference's autograd feeds into the head Linear,
+    incl. dcost) and "joint" [B,T,U,H] (the activated, optionally bf16-rounded joint tensor)."""
     if num_threads:
         torch.set_num_threads(num_threads)
     enc = enc.detach().float().cpu().clone().requires_grad_()
     dec = dec.detach().float().cpu().clone().requires_grad_()
     W = W.detach().float().cpu().clone().requires_grad_()
     bias = bias.detach().float().cpu().clone().requires_grad_()
-    logits = reference_joint_logits(enc, dec, W, bias, act, act_param, round_bf16)
+    if keep_intermediates:
+        joint = _ACTS[act](act_param)(enc[..., None, :] + dec[:, None, ...])
+        if round_bf16:
+            joint = joint + (joint.detach().to(torch.bfloat16).to(joint.dtype) - joint.detach())
+        logits = torch.nn.functional.linear(joint, W, bias)
+        logits.retain_grad()
+    else:
+        joint = None
+        logits = reference_joint_logits(enc, dec, W, bias, act, act_param, round_bf16)
     costs = reference_rnnt_abs(logits, targets.cpu(), logit_lengths.cpu(), target_lengths.cpu(), blank, "none")
     if dcost is None:
         dcost = torch.ones_like(costs)
     (costs * dcost.cpu().float()).sum().backward()
     loss = {"none": costs, "sum": costs.sum(), "mean": costs.mean()}[reduction]
-    return {"costs": costs.detach(), "loss": loss.detach(), "d_enc": enc.grad, "d_dec": dec.grad,
-            "dW": W.grad, "db": bias.grad}
+    out = {"costs": costs.detach(), "loss": loss.detach(), "d_enc": enc.grad, "d_dec": dec.grad,
+           "dW": W.grad, "db": bias.grad}
+    if keep_intermediates:
+        out["dlogits"] = logits.grad
+        out["joint"] = joint.detach()
+    return out

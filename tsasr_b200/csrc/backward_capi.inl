@@ -30,12 +30,15 @@ struct KernelTimer {
     KernelTimer() {
         static const bool enabled = getenv("TSASR_DEBUG_TIMING") != nullptr;
         on = enabled;
-        was_on = g_timing_on;
+        if (!on) return;
+        std::lock_guard<std::mutex> lock(g_timed_mu);
+        was_on = g_timing_on.load();
         first = g_n_timed;
-        if (on) g_timing_on = true;
+        g_timing_on.store(true);
     }
     ~KernelTimer() {
         if (!on) return;
+        std::lock_guard<std::mutex> lock(g_timed_mu);
         float total = 0.f;
         for (int i = first; i < g_n_timed; ++i) {
             float ms = 0.f;
@@ -48,7 +51,7 @@ struct KernelTimer {
         if (!was_on) {  // nobody will collect these events
             for (int i = first; i < g_n_timed; ++i) { cudaEventDestroy(g_timed[i].e0); cudaEventDestroy(g_timed[i].e1); }
             g_n_timed = first;
-            g_timing_on = false;
+            g_timing_on.store(false);
         }
     }
 };
@@ -187,6 +190,7 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
                     const float* alpha, const float* beta, const float* cost, const float* dcost, void* workspace,
                     size_t workspace_bytes, long long max_chunk_cells, float prune_log2_eps, float* d_enc, float* d_dec,
                     float* dW, float* db, tsasr_stream_t stream) {
+    NvtxRange nvtx_range("tsasr_joint_bwd");
     if (int rc = check_dims(B, T, U, V, blank)) return rc;
     REQUIRE(enc && dec && W && bias && logit_lengths && target_lengths && lat2 && logz && alpha && beta && cost &&
                 workspace && d_enc && d_dec && dW && db, "null pointer argument");

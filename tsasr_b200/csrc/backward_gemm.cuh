@@ -110,14 +110,15 @@ __device__ __forceinline__ void umma_bf16_2cta_x4_mnA_e(uint32_t d_tmem, uint64_
         "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, t;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first) : "memory");
 }
-// act'(x) of the pre-activation x = enc + dec, evaluated exactly as the forward does it: the derivative is
-// taken at the bf16-rounded activation output (sign for (leaky) ReLU, 1 - J^2 for tanh).
+// act'(x) of the pre-activation x = enc + dec, as the reference's autograd evaluates it (fp32, from the UNROUNDED
+// activation: torch's LeakyReLU / ReLU backward test x > 0, tanh backward is 1 - tanh(x)^2); the bf16 rounding of the
+// GEMM operand J is a straight-through step and has no derivative of its own.
 template <int ACT>
 __device__ __forceinline__ float act_grad_pre(float x, float param) {
     if (ACT == ACT_LEAKY_RELU) return x > 0.f ? 1.f : param;
     if (ACT == ACT_RELU) return x > 0.f ? 1.f : 0.f;
     if (ACT == ACT_TANH) {
-        const float j = __bfloat162float(__float2bfloat16_rn(tanhf(x)));
+        const float j = tanhf(x);
         return 1.f - j * j;
     }
     return 1.f;

@@ -7,12 +7,14 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost nothing unless a profiler is attached
 
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "backward_gemm.cuh"
 #include "common.cuh"
@@ -56,25 +58,37 @@ static int cuda_fail(cudaError_t e, const char* what) {
 
 // ---- optional per-kernel timing (measurement aid, see tsasr_kernel_timing_enable) ----
 // Every launch site is bracketed by two CUDA events on the launching stream; nothing synchronises until
-// tsasr_kernel_timings() is called.  Not thread-safe by design (bench.py / tools are single-threaded).
+// tsasr_kernel_timings() is called.  Off by default (one relaxed atomic load per launch site); while on, the record is
+// guarded by a mutex so that calls from several host threads (one per device) stay consistent.
 struct TimedLaunch { const char* name; cudaEvent_t e0, e1; };
-static bool g_timing_on = false;
+static std::atomic<bool> g_timing_on{false};
+static std::mutex g_timed_mu;
 static TimedLaunch g_timed[4096];
 static int g_n_timed = 0;
 struct ScopedTiming {
-    int idx = -1;
+    cudaEvent_t e1 = nullptr;
     cudaStream_t st;
     ScopedTiming(const char* name, cudaStream_t s) : st(s) {
-        if (!g_timing_on || g_n_timed >= 4096) return;
-        idx = g_n_timed++;
-        g_timed[idx].name = name;
-        cudaEventCreate(&g_timed[idx].e0);
-        cudaEventCreate(&g_timed[idx].e1);
-        cudaEventRecord(g_timed[idx].e0, st);
+        if (!g_timing_on.load(std::memory_order_relaxed)) return;
+        cudaEvent_t e0 = nullptr;
+        {
+            std::lock_guard<std::mutex> lock(g_timed_mu);
+            if (g_n_timed >= 4096) return;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            g_timed[g_n_timed++] = TimedLaunch{name, e0, e1};
+        }
+        cudaEventRecord(e0, st);
     }
     ~ScopedTiming() {
-        if (idx >= 0) cudaEventRecord(g_timed[idx].e1, st);
+        if (e1) cudaEventRecord(e1, st);
     }
+};
+
+// NVTX range over one C-ABI call (fwd / DP / bwd show up as named ranges in nsys / ncu timelines)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
 
 #define REQUIRE(cond, ...) \
@@ -121,19 +135,31 @@ static int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t rows, ui
     return TSASR_OK;
 }
 
+// SM count and opt-in shared memory of the CURRENT device, cached per device ordinal (one process may drive several
+// GPUs: SpeechBrain's data_parallel_backend, multi-device tests).  The cache is written once per device with the same
+// values by whoever gets there first, so concurrent callers need no lock.
 static int device_info(int* num_sms, int* max_smem) {
-    static int sms = 0, smem = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    static constexpr int kMaxDevices = 64;
+    static std::atomic<int> sms_cache[kMaxDevices];   // zero-initialised; 0 = not queried yet
+    static std::atomic<int> smem_cache[kMaxDevices];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    const bool cacheable = dev >= 0 && dev < kMaxDevices;
+    int sms = cacheable ? sms_cache[dev].load(std::memory_order_acquire) : 0, smem = 0;
+    if (sms > 0) {
+        smem = smem_cache[dev].load(std::memory_order_relaxed);
+    } else {
         int major = 0;
         cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-        if (major != 10) {
-            sms = 0;
-            return fail(TSASR_E_UNSUPPORTED, "tsasr_b200 kernels are built for sm_100a only (device is sm_%d0)", major);
+        if (major != 10)
+            return fail(TSASR_E_UNSUPPORTED, "tsasr_b200 kernels are built for sm_100a only (device %d is sm_%d0)", dev, major);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (sms <= 0) return fail(TSASR_E_CUDA, "cudaDeviceGetAttribute(MultiProcessorCount) returned %d", sms);
+        if (cacheable) {
+            smem_cache[dev].store(smem, std::memory_order_relaxed);
+            sms_cache[dev].store(sms, std::memory_order_release);
         }
     }
     *num_sms = sms;
@@ -291,11 +317,12 @@ const char* tsasr_last_error(void) { return g_err; }
 long long tsasr_launch_count(void) { return g_launches.load(); }
 
 int tsasr_kernel_timing_enable(int on) {
-    g_timing_on = on != 0;
+    g_timing_on.store(on != 0);
     return TSASR_OK;
 }
 
 int tsasr_kernel_timings(char* names, float* ms, int* counts, int max_n) {
+    std::lock_guard<std::mutex> lock(g_timed_mu);
     int n = 0;
     for (int i = 0; i < g_n_timed; ++i) {
         float t = 0.f;
@@ -326,6 +353,7 @@ size_t tsasr_lattice_elems(int B, int T, int U) { return (size_t)B * (size_t)(T 
 int tsasr_logits_to_lattice(const void* logits, int logits_dtype, const int32_t* targets, const int32_t* logit_lengths,
                             const int32_t* target_lengths, int B, int T, int U, int V, int blank, int normalized,
                             float* lat2, float* den, tsasr_stream_t stream) {
+    NvtxRange nvtx_range("tsasr_logits_to_lattice");
     if (int rc = check_dims(B, T, U, V, blank)) return rc;
     REQUIRE(logits && logit_lengths && target_lengths && lat2 && den, "null pointer argument");
     REQUIRE(U == 1 || targets, "targets must not be null when U > 1");
@@ -341,6 +369,7 @@ int tsasr_logits_to_lattice(const void* logits, int logits_dtype, const int32_t*
 int tsasr_lattice_alpha_beta(const float* lat2, const int32_t* logit_lengths, const int32_t* target_lengths, int B,
                              int T, int U, float* alpha, float* beta, float* cost, float* ll_alpha, float* ll_beta,
                              tsasr_stream_t stream) {
+    NvtxRange nvtx_range("tsasr_lattice_alpha_beta");
     if (int rc = check_dims(B, T, U, 1, 0)) return rc;
     REQUIRE(lat2 && logit_lengths && target_lengths && alpha && beta && cost && ll_alpha && ll_beta, "null pointer argument");
     if (U > 1024) return fail(TSASR_E_UNSUPPORTED, "lattice width U=%d > 1024 is not supported (the reference's Numba kernels share this limit)", U);
@@ -355,6 +384,7 @@ int tsasr_logits_grad(const void* logits, int logits_dtype, const int32_t* targe
                       const int32_t* target_lengths, int B, int T, int U, int V, int blank, const float* lat2,
                       const float* den, const float* alpha, const float* beta, const float* cost, const float* dcost,
                       float clamp, void* dlogits, tsasr_stream_t stream) {
+    NvtxRange nvtx_range("tsasr_logits_grad");
     if (int rc = check_dims(B, T, U, V, blank)) return rc;
     REQUIRE(logits && logit_lengths && target_lengths && lat2 && den && alpha && beta && cost && dlogits, "null pointer argument");
     REQUIRE(U == 1 || targets, "targets must not be null when U > 1");
@@ -384,6 +414,7 @@ int tsasr_logprobs_grad(const int32_t* targets, const int32_t* logit_lengths, co
 int tsasr_joint_fwd(const void* enc, const void* dec, const void* W, const float* bias, const int32_t* targets,
                     const int32_t* logit_lengths, const int32_t* target_lengths, int B, int T, int U, int H, int V,
                     int blank, int act_kind, float act_param, float* lat2, float* logz, tsasr_stream_t stream) {
+    NvtxRange nvtx_range("tsasr_joint_fwd");
     if (int rc = check_dims(B, T, U, V, blank)) return rc;
     REQUIRE(enc && dec && W && bias && logit_lengths && target_lengths && lat2 && logz, "null pointer argument");
     REQUIRE(U == 1 || targets, "targets must not be null when U > 1");

@@ -23,6 +23,17 @@ __host__ __device__ __forceinline__ size_t skew_index(int b, int t, int u, int T
     return ((size_t)b * (size_t)(T + U - 1) + (size_t)(t + u)) * (size_t)U + (size_t)u;
 }
 
+// Lengths as every kernel of the library reads them: clamped to the padded lattice (T_b in [1, T], label count in
+// [0, U-1]).  The fused path validates lengths on the host only AFTER queueing its kernels, and three compat entry
+// points (Transducer.apply, TransducerLoss on dense logits, rnnt_loss(check_lengths=False)) do not validate at all, so
+// an out-of-range length must never index outside the utterance's slab -- and the DP and the gradient kernels must
+// agree on the rectangle they work on.
+__device__ __forceinline__ void clamped_lengths(const int* __restrict__ logit_lengths, const int* __restrict__ target_lengths,
+                                                int b, int T, int U, int& Tb, int& Ub) {
+    Tb = min(max(logit_lengths[b], 1), T);
+    Ub = min(max(target_lengths[b], 0), U - 1) + 1;
+}
+
 // ------------------------------------------------------------------------------------------
 // Live cell tiles.  Tiles are numbered densely, tile = ((b * nTt + tt) * nTu + tu); those entirely outside the
 // utterance's T_b x U_b rectangle ("dead": ~40 % of a ragged batch) carry no data.  The kernels work on the k-th
@@ -149,17 +160,6 @@ __device__ __forceinline__ float act_apply(float x, int kind, float param) {
         default: return x;
     }
 }
-// act'(pre) expressed through the (bf16-rounded) activation output j; all supported
-// activations preserve sign, so leaky/relu only need sign(j).
-__device__ __forceinline__ float act_grad_from_output(float j, int kind, float param) {
-    switch (kind) {
-        case ACT_LEAKY_RELU: return j > 0.f ? 1.f : param;
-        case ACT_RELU: return j > 0.f ? 1.f : 0.f;
-        case ACT_TANH: return 1.f - j * j;
-        default: return 1.f;
-    }
-}
-
 __device__ __forceinline__ float logaddexp_fast(float a, float b) {
     // max + log1p(exp(-|a-b|)); -inf safe (both -inf -> -inf)
     const float m = fmaxf(a, b);
@@ -231,22 +231,46 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must never hang the GPU (a hung box is a strike).  A failed try_wait probe returns after
-// a hardware suspend of a few microseconds (measured: 2^27 probes took ~9 minutes), so 2^21 probes bound a wait to a few
-// seconds -- orders of magnitude beyond any legitimate wait of these kernels; then the CTA records the barrier id and traps.
+// Fail-stop instead of a silent hang.  A wait of these kernels lasts microseconds; a protocol bug would spin forever and
+// wedge the process (and the GPU box) until somebody resets the device.  The wait therefore carries a WALL-CLOCK bound
+// (%globaltimer, checked every 4096 failed probes): after kMbarTimeoutNs without progress the CTA records the barrier
+// id and traps, which surfaces as a CUDA error on the host.  The bound is time based -- not a probe count -- so that
+// tools that slow a kernel down by orders of magnitude (ncu replay, compute-sanitizer, a debugger, MPS time slicing)
+// stay far away from it: 30 s by default, 2 s in -DTSASR_DEBUG builds (development: fail fast), and compiled out
+// entirely with -DTSASR_NO_WATCHDOG.
+#if defined(TSASR_DEBUG)
+static constexpr unsigned long long kMbarTimeoutNs = 2000000000ull;
+#else
+static constexpr unsigned long long kMbarTimeoutNs = 30000000000ull;
+#endif
 static __device__ unsigned int g_tsasr_hang_info[4];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
+#if defined(TSASR_NO_WATCHDOG)
+    while (!mbar_try_wait(bar, parity)) {}
+#else
     uint32_t spins = 0;
+    unsigned long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 21)) {
-            g_tsasr_hang_info[0] = 0xDEAD0000u | tag;
-            g_tsasr_hang_info[1] = blockIdx.x;
-            g_tsasr_hang_info[2] = threadIdx.x;
-            g_tsasr_hang_info[3] = parity;
-            __threadfence_system();
-            __trap();
+        if ((++spins & 4095u) == 0u) {  // a failed probe already suspends the warp for a while: this is rare
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) {
+                t0 = now;
+            } else if (now - t0 > kMbarTimeoutNs) {
+                g_tsasr_hang_info[0] = 0xDEAD0000u | tag;
+                g_tsasr_hang_info[1] = blockIdx.x;
+                g_tsasr_hang_info[2] = threadIdx.x;
+                g_tsasr_hang_info[3] = parity;
+                __threadfence_system();
+                __trap();
+            }
         }
     }
+#endif
 }
 
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)

@@ -123,7 +123,8 @@ logits_to_lattice_kernel(const T* __restrict__ logits, const int* __restrict__ t
     const int u = (int)(cell % U);
     const int t = (int)((cell / U) % Tmax);
     const int b = (int)(cell / ((long long)U * Tmax));
-    const int Tb = logit_lengths[b], Ub = target_lengths[b] + 1;
+    int Tb, Ub;
+    clamped_lengths(logit_lengths, target_lengths, b, Tmax, U, Tb, Ub);  // same rectangle as the DP (common.cuh)
     if (t >= Tb || u >= Ub) return;
     const T* row = logits + (size_t)cell * V;
 
@@ -186,7 +187,7 @@ logits_to_lattice_kernel(const T* __restrict__ logits, const int* __restrict__ t
     if (lane == 0) {
         const float xb = to_float<T>(row[blank]);
         float xe = -INFINITY;
-        if (u < Ub - 1) xe = to_float<T>(row[targets[(size_t)b * (U - 1) + u]]) - lse;
+        if (u < Ub - 1) xe = to_float<T>(row[min(max(targets[(size_t)b * (U - 1) + u], 0), V - 1)]) - lse;  // label ids clamped: never read outside the row
         const size_t o = skew_index(b, t, u, Tmax, U);
         lat2[o] = make_float2(xb - lse, xe);
         den[o] = lse;
@@ -302,7 +303,8 @@ alpha_beta_kernel(const float2* __restrict__ lat2, const int* __restrict__ logit
     const int b = blockIdx.x;
     // lengths are clamped to the padded lattice: the fused path validates them on the host only after
     // launching (tsasr_b200/functional.py), so an invalid length must never index outside the slab
-    const int Tb = min(max(logit_lengths[b], 1), Tmax), Ub = min(max(target_lengths[b], 0), U - 1) + 1;
+    int Tb, Ub;
+    clamped_lengths(logit_lengths, target_lengths, b, Tmax, U, Tb, Ub);
     const size_t base = (size_t)b * (size_t)(Tmax + U - 1) * (size_t)U;
     // Each utterance's own rectangle starts at diagonal 0 of its slab: cell (t,u) -> row t+u.
     if (blockIdx.y == 0) dp_pass<false>(lat2 + base, alpha + base, Tb, Ub, U, ll_alpha + b, xchg, dp_ring);
@@ -353,7 +355,8 @@ logits_grad_kernel(const T* __restrict__ logits, const int* __restrict__ targets
     const int u = (int)(cell % U);
     const int t = (int)((cell / U) % Tmax);
     const int b = (int)(cell / ((long long)U * Tmax));
-    const int Tb = logit_lengths[b], Ub = target_lengths[b] + 1;
+    int Tb, Ub;
+    clamped_lengths(logit_lengths, target_lengths, b, Tmax, U, Tb, Ub);  // same rectangle as the DP (common.cuh)
     const T* row = logits + (size_t)cell * V;
     T* out = dlogits + (size_t)cell * V;
     const bool vec = sizeof(T) == 4 && (V & 3) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0) &&
@@ -372,8 +375,10 @@ logits_grad_kernel(const T* __restrict__ logits, const int* __restrict__ targets
         }
         return;
     }
+    // torchaudio's order (ComputeGradients, then `grad * dy` in the autograd backward, functional.py:1729-1734): the
+    // gradient of the UNIT cost is clamped, the upstream factor dcost[b] (1/B under reduction="mean") multiplies after.
     const float dy = dcost ? dcost[b] : 1.f;
-    const CellTerms ct = cell_terms(lat2, alpha, beta, -cost[b], dy, b, t, u, Tb, Ub, Tmax, U);
+    const CellTerms ct = cell_terms(lat2, alpha, beta, -cost[b], 1.f, b, t, u, Tb, Ub, Tmax, U);
     const float nd = -den[skew_index(b, t, u, Tmax, U)] * kLog2e;
     const int label = u < Ub - 1 ? targets[(size_t)b * (U - 1) + u] : -1;
     auto grad = [&](float x, int v) {
@@ -381,7 +386,7 @@ logits_grad_kernel(const T* __restrict__ logits, const int* __restrict__ targets
         if (v == blank) g -= ct.ob;
         if (v == label) g -= ct.oe;
         if (clamp > 0.f) g = fminf(fmaxf(g, -clamp), clamp);
-        return g;
+        return g * dy;
     };
     if (vec) {
         const float4* r4 = reinterpret_cast<const float4*>(row);
@@ -448,13 +453,14 @@ logprobs_grad_kernel(const int* __restrict__ targets, const int* __restrict__ lo
     const int u = (int)(cell % U);
     const int t = (int)((cell / U) % Tmax);
     const int b = (int)(cell / ((long long)U * Tmax));
-    const int Tb = logit_lengths[b], Ub = target_lengths[b] + 1;
+    int Tb, Ub;
+    clamped_lengths(logit_lengths, target_lengths, b, Tmax, U, Tb, Ub);  // same rectangle as the DP (common.cuh)
     if (t >= Tb || u >= Ub) return;
     const float dy = dcost ? dcost[b] : 1.f;
     const CellTerms ct = cell_terms(lat2, alpha, beta, -cost[b], dy, b, t, u, Tb, Ub, Tmax, U);
     float* g = grads + (size_t)cell * V;
     if (t < Tb - 1 || u == Ub - 1) g[blank] = -ct.ob;
-    if (u < Ub - 1) g[targets[(size_t)b * (U - 1) + u]] = -ct.oe;
+    if (u < Ub - 1) g[min(max(targets[(size_t)b * (U - 1) + u], 0), V - 1)] = -ct.oe;  // label ids clamped: never write outside the row
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -487,12 +493,11 @@ cudaError_t launch_alpha_beta(const float2* lat2, const int* ll, const int* tl, 
                               float* beta, float* ll_alpha, float* ll_beta, float* cost, cudaStream_t st) {
     const int threads = ((U + 31) / 32) * 32;
     const size_t ring_bytes = (size_t)kDpPrefetch * threads * sizeof(float2);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDpPrefetch * 1024 * (int)sizeof(float2));
-        attr_set = true;
-    }
-    cudaError_t e = launch_pdl(alpha_beta_kernel, dim3(B, 2), dim3(threads), ring_bytes, st, lat2, ll, tl, Tmax, U, alpha, beta,
+    // per launch, like the GEMM launchers: the attribute is per DEVICE, and one process may drive several GPUs
+    cudaError_t e = cudaFuncSetAttribute(alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kDpPrefetch * 1024 * (int)sizeof(float2));
+    if (e != cudaSuccess) return e;
+    e = launch_pdl(alpha_beta_kernel, dim3(B, 2), dim3(threads), ring_bytes, st, lat2, ll, tl, Tmax, U, alpha, beta,
                                ll_alpha, ll_beta);
     if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return e;
     e = launch_pdl(finalize_cost_kernel, dim3((B + 127) / 128), dim3(128), 0, st, (const float*)ll_beta, cost, B);

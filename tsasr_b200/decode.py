@@ -93,7 +93,10 @@ def fused_joint_forward_step(tjoint, classifier_network, softmax):
 
     def step(h_i, out_PN):
         with torch.no_grad():
-            if not (h_i.is_cuda and lin.weight.is_cuda) or lin.weight.shape[1] % 4 != 0:
+            H = lin.weight.shape[1]
+            fp32 = h_i.dtype == out_PN.dtype == lin.weight.dtype == torch.float32
+            if not (h_i.is_cuda and lin.weight.is_cuda) or H % 4 != 0 or H > 1536 or not fp32:
+                # shapes / dtypes the kernel does not implement (it is fp32 in, fp32 out, H <= 1536): the reference's own chain
                 out = tjoint(h_i, out_PN)
                 for layer in classifier_network:
                     out = layer(out)

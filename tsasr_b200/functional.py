@@ -16,6 +16,19 @@ def _check_reduction(reduction):
         raise ValueError('reduction should be one of "none", "mean", or "sum"')
 
 
+MAX_LATTICE_WIDTH = 1024  # alpha_beta_kernel: one thread per lattice column (the reference's Numba kernels share this limit)
+
+
+def _check_lattice_shape(U, V):
+    """Limits of the sm_100a kernels, rejected where the call is made -- not three launches later inside the C library."""
+    if U > MAX_LATTICE_WIDTH:
+        raise NotImplementedError(
+            f"tsasr_b200: lattice width U = max target length + 1 = {U} exceeds {MAX_LATTICE_WIDTH} (one DP thread per "
+            "lattice column); split the utterance or shorten the targets")
+    if V < 2:
+        raise ValueError(f"tsasr_b200: the vocabulary must hold the blank and at least one label (got V = {V})")
+
+
 def _reduce(costs, reduction):
     # torchaudio/functional/functional.py:1791-1794: reduction is applied OUTSIDE the autograd
     # Function, so "mean" back-propagates 1/B.
@@ -153,6 +166,7 @@ def rnnt_loss(logits, targets, logit_lengths, target_lengths, blank=-1, clamp=-1
         blank += V  # torchaudio accepts negative indices (default -1)
     if not 0 <= blank < V:
         raise RuntimeError("blank must be within [0, logits.shape[-1])")
+    _check_lattice_shape(U, max(V, 2))  # V = 1 (blank only) is legal for torchaudio and for the compat kernels
     if check_lengths:
         _validate_lengths(logit_lengths, target_lengths, T, U, targets.shape[1])
     if not fused_log_softmax:
@@ -177,6 +191,7 @@ class NumbaSemanticsTransducer(torch.autograd.Function):
         if labels.dtype != torch.int32 or T.dtype != torch.int32 or U.dtype != torch.int32:
             raise TypeError("labels, T and U must be int32 (the reference kernels are typed int32)")
         Bn, maxT, maxU, A = log_probs.shape
+        _check_lattice_shape(maxU, max(A, 2))
         log_probs = log_probs.contiguous()
         lat2, _ = ops.logits_to_lattice(log_probs, labels, T, U, blank, normalized=True)
         alpha, beta, cost, _, _ = ops.alpha_beta(lat2, T, U, Bn, maxT, maxU)
@@ -298,6 +313,7 @@ def fused_joint_rnnt_loss(enc_out, dec_out, weight, bias, targets, logit_lengths
         raise ValueError("shape mismatch between enc_out, dec_out and weight")
     if not (enc_out.is_cuda and logit_lengths.is_cuda and target_lengths.is_cuda):
         raise ValueError("tsasr_b200 needs CUDA tensors; there is no CPU path")
+    _check_lattice_shape(U, V)
     if bias is None:
         bias = torch.zeros((V,), dtype=torch.float32, device=enc_out.device)
     if blank < 0:

@@ -123,19 +123,31 @@ def joint_fwd(enc, dec, W, bias, targets, logit_lengths, target_lengths, blank, 
     return lat2, logz
 
 
-_workspaces = {}
+_workspaces = {}          # (device, stream handle) -> uint8 workspace tensor, least recently used first
+_MAX_CACHED_WORKSPACES = 4  # per process: a stream that stops running backward passes gives its buffer back
 
 
 def _workspace(dev, nbytes):
     """Cached workspace per (device, stream) -- two backward passes queued on different streams of one device must not
-    share their operand images -- grown on demand; the torch caching allocator owns the memory."""
+    share their operand images -- grown on demand; the torch caching allocator owns the memory.  The cache is bounded
+    (least recently used entries are dropped, their memory returns to the allocator once the queued kernels are done:
+    the allocator is stream-aware) and a buffer that is outgrown is released BEFORE its replacement is allocated."""
     key = (dev, torch.cuda.current_stream(dev).cuda_stream)
-    ws = _workspaces.get(key)
+    ws = _workspaces.pop(key, None)
     if ws is None or ws.numel() < nbytes:
-        ws = None
-        _workspaces[key] = None
+        last = _last_bwd.get(dev)
+        if last is not None and last[0] is ws:  # the statistics accessor must not pin the outgrown buffer
+            del _last_bwd[dev]
+        ws = last = None
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-        _workspaces[key] = ws
+    _workspaces[key] = ws  # most recently used last
+    while len(_workspaces) > _MAX_CACHED_WORKSPACES:
+        old_key = next(iter(_workspaces))
+        old = _workspaces.pop(old_key)
+        last = _last_bwd.get(old_key[0])
+        if last is not None and last[0] is old:
+            del _last_bwd[old_key[0]]
+        del old, last
     return ws
 
 

@@ -25,6 +25,15 @@ from . import _lib
 logger = logging.getLogger(__name__)
 
 _MIN_DEFERRED_CELLS = 2  # a single cell (decode-time [B,1,1,H] calls) uses the eager math
+MAX_FUSED_H = 640        # kMaxKB * 64 (csrc/joint_gemm.cuh): the A operand of a cell tile is shared-memory resident
+_warned = set()
+
+
+def _warn_once(msg):
+    """One warning per distinct message and process: a shape the fused path does not cover must not degrade silently."""
+    if msg not in _warned:
+        _warned.add(msg)
+        logger.warning("tsasr_b200: %s", msg)
 
 
 def activation_code(module):
@@ -80,7 +89,8 @@ class JointHandle(torch.Tensor):
             if isinstance(x, JointHandle) and not x.has_head:
                 w = args[1] if len(args) > 1 else kwargs.get("weight")
                 b = args[2] if len(args) > 2 else kwargs.get("bias")
-                if isinstance(w, torch.Tensor) and not isinstance(w, JointHandle) and w.dim() == 2 and w.shape[1] == x.shape[-1]:
+                if (isinstance(w, torch.Tensor) and not isinstance(w, JointHandle) and w.dim() == 2 and w.shape[1] == x.shape[-1]
+                        and w.shape[0] >= 2):  # V = 1 (blank only) has no fused kernel: materialise
                     return JointHandle(x._enc, x._dec, x._act_module, x._act_code, x._act_param, w, b)
         name = getattr(func, "__name__", "")
         if name == "__get__" or func in _METADATA_FUNCS:
@@ -144,7 +154,12 @@ class Transducer_joint(nn.Module):
         if input_TN.shape[2] != 1 or input_PN.shape[1] != 1 or input_TN.shape[0] != input_PN.shape[0]:
             return None
         H = input_TN.shape[3]
-        if input_PN.shape[3] != H or not 1 <= H <= 640:  # H % 64 != 0 is zero-padded to whole k-blocks by the fused op
+        if input_PN.shape[3] != H or H < 1:
+            return None
+        if H > MAX_FUSED_H:  # H % 64 != 0 is zero-padded to whole k-blocks by the fused op
+            _warn_once(f"joint dimension H = {H} > {MAX_FUSED_H}: the fused tcgen05 path keeps the whole joint operand of a cell "
+                       "tile in shared memory and does not implement this width; falling back to the reference's eager math "
+                       "(materialised [B,T,U,H] / [B,T,U,V] tensors, cuBLAS GEMMs, compat loss kernels)")
             return None
         if input_TN.shape[1] * input_PN.shape[2] < _MIN_DEFERRED_CELLS:
             return None
