@@ -91,7 +91,7 @@ def act_grad(enc, dec, act, act_param):
     return torch.ones_like(x)
 
 
-def backward_from_operands(dlogits, joint, W, enc, dec, act, act_param, mask, dtype=torch.float64, with_bounds=True):
+def backward_from_operands(dlogits, joint, W, enc, dec, act, act_param, mask, dtype=torch.float64, with_bounds=True, with_sq=True):
     """float64 restatement of autograd through Linear (SB/nnet/linear.py:74), the activation and the broadcast add
     (SB/nnet/transducer/transducer_joint.py:74,95) on GIVEN dlogits / joint operands.  mask [B,T,U] zeroes cells that
     carry no data.  Returns dict(d_enc, d_dec, dW, db) plus the matching sums of |terms| ("abs_*") and of squared
@@ -114,6 +114,7 @@ def backward_from_operands(dlogits, joint, W, enc, dec, act, act_param, mask, dt
         dJ_abs = (dYa @ Wd.abs()).reshape(B, T, U, H) * g.abs()
         out["abs_d_enc"], out["abs_d_dec"] = dJ_abs.sum(2), dJ_abs.sum(1)
         del dJ_abs, dYa
+    if with_bounds and with_sq:
         dYs = dY2 * dY2
         out["sq_dW"] = dYs.t() @ (J2 * J2)
         out["sq_db"] = dYs.sum(0)

@@ -53,7 +53,7 @@ def _rel(got, ref):
 
 @pytest.mark.timeout(600)
 def test_config2_single_full_size_utterance_vs_reference_chain():
-    """B=1 at the full T, U, V, H of configs[1]: per-utterance loss 1e-4 relative, operand gradients 1e-2 of max."""
+    """B=1 at the full T, U, V, H of configs[1]: per-utterance loss 1e-4 relative, operand gradients 3e-3 of max (+ fp32 lattice floor)."""
     B, T, U, H, V = 1, 400, 100, 640, 1000
     enc, dec, W, b, targets, ll, tl = _inputs(B, T, U, H, V, seed=11, ragged=False)
     dcost = torch.ones(B)
@@ -62,7 +62,10 @@ def test_config2_single_full_size_utterance_vs_reference_chain():
     np.testing.assert_allclose(costs.cpu().numpy(), ref["costs"].numpy(), rtol=1e-4)
     errs = {"d_enc": _rel(d_enc.cpu(), ref["d_enc"]), "d_dec": _rel(d_dec.cpu(), ref["d_dec"]),
             "dW": _rel(dW.cpu(), ref["dW"]), "db": _rel(db.cpu(), ref["db"])}
-    assert all(v < 1e-2 for v in errs.values()), errs
+    # 3e-3 of the largest entry + the floor an fp32 lattice of this size imposes on any implementation, the reference
+    # included (tools/fp32_noise_floor.py; elementwise bounds: test_parity_tight_gpu.py)
+    floor = 0.5 * 2.0 ** -23 * float(ref["costs"].abs().max()) * (T + U) ** 0.5
+    assert all(v < 3e-3 + floor for v in errs.values()), (errs, floor)
 
 
 def _properties(B, T, U, H, V, seed, max_chunk_cells=0):

@@ -1,0 +1,156 @@
+"""Robustness tests of the C ABI on the GPU (round-2 additions): out-of-range lengths on the entry points that do not
+validate them, torchaudio's clamp order, guard bands around every output buffer (compute-sanitizer is closed on this
+pool -- see profiles/r2_sanitizer_status.txt -- so overruns are looked for with canaries), early shape errors."""
+import numpy as np
+import pytest
+import torch
+
+import tsasr_b200
+from tsasr_b200 import _lib, ops
+from tsasr_b200.functional import NumbaSemanticsTransducer
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def test_out_of_range_lengths_on_unvalidated_entry_points_are_clamped():
+    """Transducer.apply / TransducerLoss on dense logits / rnnt_loss(check_lengths=False) perform no host-side length
+    validation (neither does the reference).  T_b > T or a label count > U-1 must behave exactly like the clamped
+    lengths in EVERY kernel (DP and gradient on the same rectangle), never index outside the utterance's slab."""
+    g = torch.Generator().manual_seed(3)
+    B, T, U, V = 3, 11, 6, 17
+    logits = torch.randn(B, T, U, V, generator=g)
+    targets = torch.randint(1, V, (B, U - 1), generator=g, dtype=torch.int32)
+    bad_T = torch.tensor([T + 7, T, 0], dtype=torch.int32)
+    bad_U = torch.tensor([U - 1, U + 40, -2], dtype=torch.int32)
+    ok_T = torch.tensor([T, T, 1], dtype=torch.int32)
+    ok_U = torch.tensor([U - 1, U - 1, 0], dtype=torch.int32)
+    d = _dev()
+    outs = []
+    for Tl, Ul in ((bad_T, bad_U), (ok_T, ok_U)):
+        lp = logits.to(d).log_softmax(-1).requires_grad_()
+        loss = NumbaSemanticsTransducer.apply(lp, targets.to(d), Tl.to(d), Ul.to(d), 0, "none")
+        loss.sum().backward()  # the VALUE divides by the T the caller passed (transducer_loss.py:104-106): gradients are compared
+        x = logits.to(d).requires_grad_()
+        costs = tsasr_b200.rnnt_loss(x, targets.to(d), Tl.to(d), Ul.to(d), blank=0, reduction="none", check_lengths=False)
+        costs.sum().backward()
+        torch.cuda.synchronize()
+        outs.append((lp.grad.cpu(), costs.detach().cpu(), x.grad.cpu()))
+    (g_bad, c_bad, x_bad), (g_ok, c_ok, x_ok) = outs
+    assert torch.equal(g_bad, g_ok) and torch.equal(c_bad, c_ok) and torch.equal(x_bad, x_ok)
+    assert torch.isfinite(c_ok).all()
+
+
+@pytest.mark.parametrize("reduction", ["mean", "sum", "none"])
+def test_clamp_is_applied_to_the_unit_gradient_like_torchaudio(reduction):
+    """torchaudio clamps the gradient of the UNIT cost and multiplies by grad_output afterwards
+    (functional.py:1729-1734): with reduction="mean" the threshold must not become B times looser."""
+    from torchaudio.functional import rnnt_loss as ta_rnnt_loss
+
+    g = torch.Generator().manual_seed(9)
+    B, T, U, V = 4, 13, 5, 11
+    logits = 3.0 * torch.randn(B, T, U, V, generator=g)
+    targets = torch.randint(1, V, (B, U - 1), generator=g, dtype=torch.int32)
+    ll = torch.tensor([T, T - 2, T - 5, T], dtype=torch.int32)
+    tl = torch.tensor([U - 1, 2, U - 1, 1], dtype=torch.int32)
+    clamp = 0.05
+    ref_x = logits.clone().requires_grad_()
+    ref = ta_rnnt_loss(ref_x, targets, ll, tl, blank=0, clamp=clamp, reduction=reduction)
+    (ref.sum() if ref.dim() else ref).backward()
+    d = _dev()
+    x = logits.to(d).requires_grad_()
+    got = tsasr_b200.rnnt_loss(x, targets.to(d), ll.to(d), tl.to(d), blank=0, clamp=clamp, reduction=reduction)
+    (got.sum() if got.dim() else got).backward()
+    np.testing.assert_allclose(got.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-4)
+    scale = 1.0 / B if reduction == "mean" else 1.0
+    assert ref_x.grad.abs().max().item() == pytest.approx(clamp * scale, rel=1e-6)  # the clamp is active in this case
+    assert (x.grad.cpu() - ref_x.grad).abs().max().item() < 1e-3 * scale + 1e-6
+
+
+def _guarded(n_bytes, guard=4096):
+    """(whole uint8 buffer, 1024-aligned payload view of n_bytes) with `guard` canary bytes on either side."""
+    buf = torch.full((n_bytes + 2 * guard + 2048,), 0xA5, dtype=torch.uint8, device=_dev())
+    start = guard + (-(buf.data_ptr() + guard)) % 1024
+    return buf, buf[start: start + n_bytes], start
+
+
+def _guards_intact(buf, start, n_bytes):
+    return bool((buf[:start] == 0xA5).all()) and bool((buf[start + n_bytes:] == 0xA5).all())
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 9, 64, 40), (3, 37, 19, 128, 300), (2, 50, 33, 640, 1031), (1, 9, 130, 192, 257)])
+@pytest.mark.parametrize("chunk", [0, 128 * 3])
+def test_no_kernel_writes_outside_its_buffers(shape, chunk):
+    """Every output and the workspace of the fused path sit between canary bands (raw C-ABI calls, exact sizes from
+    the header's contracts): forward, DP and a chunked backward must leave all bands intact."""
+    B, T, U, H, V = shape
+    lib = _lib.load()
+    d = _dev()
+    g = torch.Generator().manual_seed(sum(shape))
+    enc = (0.5 * torch.randn(B, T, H, generator=g)).bfloat16().to(d)
+    dec = (0.5 * torch.randn(B, U, H, generator=g)).bfloat16().to(d)
+    W = ((torch.rand(V, H, generator=g) * 2 - 1) / H ** 0.5).bfloat16().to(d)
+    bias = ((torch.rand(V, generator=g) * 2 - 1) / H ** 0.5).to(d)
+    targets = torch.randint(1, V, (B, U - 1), generator=g, dtype=torch.int32).to(d)
+    ll = torch.randint(max(1, T // 2), T + 1, (B,), generator=g, dtype=torch.int32)
+    tl = torch.randint(0, U, (B,), generator=g, dtype=torch.int32)
+    ll[0], tl[0] = T, U - 1
+    ll, tl = ll.to(d), tl.to(d)
+    dcost = torch.ones(B, device=d)
+    n = ops.lattice_elems(B, T, U)
+    st = torch.cuda.current_stream(d).cuda_stream
+    ws_bytes = int(lib.tsasr_joint_bwd_workspace_bytes(B, T, U, H, V, chunk))
+    sizes = {"lat2": 8 * n, "logz": 4 * n, "alpha": 4 * n, "beta": 4 * n, "cost": 4 * B, "lla": 4 * B, "llb": 4 * B,
+             "d_enc": 4 * B * T * H, "d_dec": 4 * B * U * H, "dW": 4 * V * H, "db": 4 * V, "ws": ws_bytes}
+    bufs = {k: _guarded(v) for k, v in sizes.items()}
+    p = {k: v[1].data_ptr() for k, v in bufs.items()}
+    _lib.check(lib.tsasr_joint_fwd(enc.data_ptr(), dec.data_ptr(), W.data_ptr(), bias.data_ptr(), targets.data_ptr(), ll.data_ptr(),
+                                   tl.data_ptr(), B, T, U, H, V, 0, 0, 0.01, p["lat2"], p["logz"], st))
+    _lib.check(lib.tsasr_lattice_alpha_beta(p["lat2"], ll.data_ptr(), tl.data_ptr(), B, T, U, p["alpha"], p["beta"], p["cost"],
+                                            p["lla"], p["llb"], st))
+    _lib.check(lib.tsasr_joint_bwd(enc.data_ptr(), dec.data_ptr(), W.data_ptr(), bias.data_ptr(), targets.data_ptr(), ll.data_ptr(),
+                                   tl.data_ptr(), B, T, U, H, V, 0, 0, 0.01, p["lat2"], p["logz"], p["alpha"], p["beta"], p["cost"],
+                                   dcost.data_ptr(), p["ws"], ws_bytes, chunk, -30.0, p["d_enc"], p["d_dec"], p["dW"], p["db"], st))
+    torch.cuda.synchronize()
+    for k, (buf, view, start) in bufs.items():
+        assert _guards_intact(buf, start, sizes[k]), f"canary band around {k} was overwritten"
+    cost = bufs["cost"][1].view(torch.float32)
+    assert torch.isfinite(cost).all() and (cost > 0).all()
+    assert torch.isfinite(bufs["dW"][1].view(torch.float32)).all()
+
+
+def test_unsupported_shapes_fail_where_the_call_is_made():
+    d = _dev()
+    U = 1030  # > 1024 lattice columns
+    enc = torch.zeros(1, 4, 64, device=d)
+    dec = torch.zeros(1, U, 64, device=d)
+    W = torch.zeros(8, 64, device=d)
+    with pytest.raises(NotImplementedError, match="lattice width"):
+        tsasr_b200.fused_joint_rnnt_loss(enc, dec, W, None, torch.zeros(1, U - 1, dtype=torch.int32, device=d),
+                                         torch.tensor([4], dtype=torch.int32, device=d), torch.tensor([U - 1], dtype=torch.int32, device=d))
+    with pytest.raises(NotImplementedError, match="lattice width"):
+        tsasr_b200.rnnt_loss(torch.zeros(1, 2, U, 3, device=d), torch.zeros(1, U - 1, dtype=torch.int32, device=d),
+                             torch.tensor([2], dtype=torch.int32, device=d), torch.tensor([U - 1], dtype=torch.int32, device=d), check_lengths=False)
+    # a head with a single output (blank only) is not deferred: the handle materialises with the eager math
+    joiner = tsasr_b200.Transducer_joint()
+    h = joiner(torch.zeros(1, 3, 1, 64, device=d), torch.zeros(1, 1, 2, 64, device=d))
+    out = torch.nn.functional.linear(h, torch.zeros(1, 64, device=d))
+    assert not isinstance(out, tsasr_b200.JointHandle) and out.shape == (1, 3, 2, 1)
+
+
+def test_two_devices_in_one_process_use_their_own_launch_attributes():
+    """cudaFuncSetAttribute is per device: a wide lattice (ring > 48 KB of dynamic shared memory) must
+    launch on a second GPU of the same process."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    B, T, U, V = 1, 3, 900, 5
+    for idx in (0, 1):
+        d = torch.device("cuda", idx)
+        logits = torch.zeros(B, T, U, V, device=d)
+        costs = tsasr_b200.rnnt_loss(logits, torch.ones(B, U - 1, dtype=torch.int32, device=d),
+                                     torch.tensor([T], dtype=torch.int32, device=d), torch.tensor([U - 1], dtype=torch.int32, device=d), blank=0,
+                                     reduction="none")
+        assert torch.isfinite(costs).all()

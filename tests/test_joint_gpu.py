@@ -88,7 +88,8 @@ def _rel_err(got, ref):
     return (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-12)
 
 
-GRAD_REL = 1e-2  # operand gradients: bf16 dlogits/J operands (2^-9 relative each), fp32 accumulation
+GRAD_REL = 3e-3  # max |err| / max |ref| of the operand gradients (bf16 dlogits / J operands, fp32 accumulation); the elementwise
+                 # bounds and the fp64 redo of the GEMMs on the decoded operand images live in test_parity_tight_gpu.py
 
 
 def _choose_tile_log2(T, U):
@@ -378,7 +379,7 @@ def test_fused_path_blank_anywhere_in_the_vocabulary(V, blank):
 def test_fused_path_fuzz_vs_compat_path():
     """Random shapes, ragged lengths, activations, chunk sizes: the fused tcgen05 path (tile pruning on) against the
     compat kernels (materialised logits built by torch from the same bf16-rounded operands; themselves pinned on the
-    C oracle and the golden vectors in test_lattice_gpu.py).  Loss 1e-4 relative, gradients 1e-2 of their largest entry."""
+    C oracle and the golden vectors in test_lattice_gpu.py).  Loss 1e-4 relative, gradients 3e-3 of their largest entry (same DP kernel on both sides: no fp32 lattice floor between them)."""
     from oracle.reference_chain import reference_joint_logits
 
     d = _dev()

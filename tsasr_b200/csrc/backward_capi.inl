@@ -67,6 +67,7 @@ static void plan_bwd(const JointParams& jp, int num_sms, long long max_chunk_cel
     const size_t tile_bytes = (size_t)(pl->NT4 + jp.KB) * kImgBytes + (size_t)(tT + tU) * jp.H * 4;
     long long want_tiles = max_chunk_cells > 0 ? max_chunk_cells / 128 : (long long)(kDefaultChunkBytes / tile_bytes);
     if (want_tiles < 1) want_tiles = 1;
+    if (want_tiles > total_tiles) want_tiles = total_tiles;  // before the narrowing below: max_chunk_cells is a 64-bit count
     int groups = (int)(want_tiles / jp.nTu);
     if (groups < 1) groups = 1;
     pl->chunk_tiles = groups * jp.nTu;
