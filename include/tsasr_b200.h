@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TSASR_ABI_VERSION 2
+#define TSASR_ABI_VERSION 3
 
 enum {
     TSASR_OK = 0,
@@ -109,6 +109,9 @@ size_t tsasr_joint_bwd_workspace_bytes(int B, int T, int U, int H, int V, long l
  * prune_log2_eps < 0: 128-cell tiles whose largest alignment posterior exp(alpha + beta - L) is below
  * 2^prune_log2_eps are left out of the backward (every term of their dlogits carries that factor; at -30 what is
  * dropped is below fp32 resolution next to the O(1) terms of the alignment band).  >= 0: every live tile is processed.
+ * clamp > 0: torchaudio's rnnt_loss(clamp=...) -- the dlogits of the UNIT cost are clamped to [-clamp, clamp] before the
+ * upstream factor dcost[b] multiplies them (ComputeGradients, then `grad * dy`: torchaudio/functional/functional.py:1729-1734),
+ * inside the gradient pass (a separate kernel instantiation: the default path pays nothing).  <= 0: off.
  * tsasr_joint_bwd_stats_offset(): byte offset, from the workspace base rounded up to 1024, of three int32
  * {active tiles of the last chunk, active tiles, live tiles} written by the call (measurement aid). */
 size_t tsasr_joint_bwd_stats_offset(int B, int T, int U, int H, int V, long long max_chunk_cells);
@@ -116,8 +119,8 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
                     const int32_t* logit_lengths, const int32_t* target_lengths, int B, int T, int U, int H, int V,
                     int blank, int act_kind, float act_param, const float* lat2, const float* logz,
                     const float* alpha, const float* beta, const float* cost, const float* dcost, void* workspace,
-                    size_t workspace_bytes, long long max_chunk_cells, float prune_log2_eps, float* d_enc, float* d_dec,
-                    float* dW, float* db, tsasr_stream_t stream);
+                    size_t workspace_bytes, long long max_chunk_cells, float prune_log2_eps, float clamp, float* d_enc,
+                    float* d_dec, float* dW, float* db, tsasr_stream_t stream);
 
 /* ---- host-path helpers of the fused loss (one launch each instead of a dozen elementwise launches) -------
  * tsasr_prepare_lengths: the integer length conversion of SB/nnet/losses.py:58-59, bit-exact

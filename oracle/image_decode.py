@@ -97,8 +97,9 @@ def backward_from_operands(dlogits, joint, W, enc, dec, act, act_param, mask, dt
     carry no data.  Returns dict(d_enc, d_dec, dW, db) plus the matching sums of |terms| ("abs_*") and of squared
     terms ("sq_*") used for elementwise error bounds."""
     m = mask[..., None].to(dtype)
-    dY = dlogits.to(dtype) * m
-    J = joint.to(dtype) * m
+    zero = torch.zeros((), dtype=dtype)
+    dY = torch.where(mask[..., None], dlogits.to(dtype), zero)   # not a product: unwritten tiles may hold NaN / Inf bit patterns
+    J = torch.where(mask[..., None], joint.to(dtype), zero)
     Wd = W.to(dtype)
     B, T, U, V = dY.shape
     H = J.shape[-1]

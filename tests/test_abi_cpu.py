@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/tsasr_b200.h but not exported"
     assert set(declared) == set(_lib.SIGNATURES), "ctypes binding and header disagree"
-    assert _lib.load().tsasr_abi_version() == 2
+    assert _lib.load().tsasr_abi_version() == _lib.ABI_VERSION == 3
     assert _lib.load().tsasr_lattice_elems(2, 5, 3) == 2 * 7 * 3
 
 

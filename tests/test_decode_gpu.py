@@ -104,3 +104,39 @@ def test_patch_searcher_swaps_only_supported_chains():
     two_layers = types.SimpleNamespace(tjoint=tsasr_b200.Transducer_joint(joint="sum"), classifier_network=[head, head],
                                        softmax=torch.nn.LogSoftmax(dim=-1))
     assert not decode.patch_searcher(two_layers)
+
+
+def test_on_device_greedy_bookkeeping_reproduces_reference_searcher_cpu(golden):
+    """CPU (no kernels involved): the device-side bookkeeping of ``greedy_decode_on_device`` -- masked select instead of
+    per-utterance ``.item()`` branches -- gives exactly the reference searcher's hypotheses and score."""
+    g = golden("greedy_decode")
+    pred, head, tjoint, tn, hyps = _golden_modules(g, "cpu")
+    step = eager_joint_step(tjoint, [head], torch.nn.LogSoftmax(dim=-1))
+    got, score, a, b = decode.greedy_decode_on_device(tn, pred.layers(), step, blank_id=0)
+    assert got == hyps and a is None and b is None
+    np.testing.assert_allclose(float(score), float(g["mean_exp_score"]), rtol=1e-4)
+
+
+@pytest.mark.gpu
+def test_on_device_greedy_with_fused_step_vs_reference_golden(golden):
+    """The whole greedy search on the GPU: fused joint step + on-device bookkeeping; ONE device->host copy at the end.
+    Hypotheses bit-exact against the vector produced by the reference's own searcher class."""
+    g = golden("greedy_decode")
+    d = torch.device("cuda:0")
+    pred, head, tjoint, tn, hyps = _golden_modules(g, d)
+    torch.backends.cudnn.allow_tf32 = False
+    searcher = types.SimpleNamespace(tjoint=tjoint, classifier_network=[head], softmax=torch.nn.LogSoftmax(dim=-1),
+                                     decode_network_lst=pred.layers(), blank_id=0, beam_size=1)
+    assert decode.patch_searcher(searcher, on_device_greedy=True)
+    launches0 = tsasr_b200._lib.launch_count()
+    got, score, _, _ = searcher.searcher(tn)
+    assert tsasr_b200._lib.launch_count() - launches0 == 2 * tn.shape[1]
+    assert got == hyps
+    np.testing.assert_allclose(float(score), float(g["mean_exp_score"]), rtol=1e-4)
+    # and it agrees with the per-frame-sync loop on a larger random problem (same modules, same fused step)
+    gen = torch.Generator().manual_seed(5)
+    tn2 = (1.5 * torch.randn(6, 120, tn.shape[2], generator=gen)).to(d)
+    ref_h, ref_s = greedy_decode(tn2, pred.layers(), searcher._joint_forward_step)
+    got_h, got_s, _, _ = searcher.searcher(tn2)
+    assert got_h == ref_h
+    np.testing.assert_allclose(float(got_s), np.exp(np.array(ref_s)).mean(), rtol=1e-4)

@@ -154,3 +154,36 @@ def test_two_devices_in_one_process_use_their_own_launch_attributes():
                                      torch.tensor([T], dtype=torch.int32, device=d), torch.tensor([U - 1], dtype=torch.int32, device=d), blank=0,
                                      reduction="none")
         assert torch.isfinite(costs).all()
+
+
+@pytest.mark.parametrize("reduction", ["mean", "sum"])
+def test_fused_path_clamp_matches_the_compat_kernels(reduction):
+    """torchaudio's ``clamp`` on the fused path (MODE_GRAD_CLAMP instantiation of the gradient pass): same operand
+    gradients as the compat kernels with the same clamp on the materialised logits (those are pinned on torchaudio above),
+    and the clamp does bite in this case."""
+    from oracle.reference_chain import reference_joint_logits
+
+    d = _dev()
+    g = torch.Generator().manual_seed(31)
+    B, T, U, H, V = 3, 37, 14, 128, 300
+    enc = (0.5 * torch.randn(B, T, H, generator=g)).bfloat16().float()
+    dec = (0.5 * torch.randn(B, U, H, generator=g)).bfloat16().float()
+    W = (4.0 * (torch.rand(V, H, generator=g) * 2 - 1) / H ** 0.5).bfloat16().float()   # peaky softmax: large dlogits entries
+    b = (torch.rand(V, generator=g) * 2 - 1) / H ** 0.5
+    targets = torch.randint(1, V, (B, U - 1), generator=g, dtype=torch.int32)
+    ll = torch.tensor([T, T - 9, T - 20], dtype=torch.int32)
+    tl = torch.tensor([U - 1, 5, U - 1], dtype=torch.int32)
+    clamp = 0.02
+    outs = {}
+    for c in (clamp, -1.0):
+        e, dc, w, bb = (x.to(d).requires_grad_() for x in (enc, dec, W, b))
+        loss = tsasr_b200.fused_joint_rnnt_loss(e, dc, w, bb, targets.to(d), ll.to(d), tl.to(d), blank=0, reduction=reduction, clamp=c)
+        loss.backward()
+        outs[c] = [x.grad.clone() for x in (e, dc, w, bb)]
+    e2, dc2, w2, bb2 = (x.to(d).requires_grad_() for x in (enc, dec, W, b))
+    logits = reference_joint_logits(e2, dc2, w2, bb2, "leaky_relu", 0.01, round_bf16=True)
+    loss2 = tsasr_b200.rnnt_loss(logits.contiguous(), targets.to(d), ll.to(d), tl.to(d), blank=0, clamp=clamp, reduction=reduction)
+    loss2.backward()
+    for got, ref, free in zip(outs[clamp], (e2.grad, dc2.grad, w2.grad, bb2.grad), outs[-1.0]):
+        assert ((got - ref).abs().max() / ref.abs().max()).item() < 3e-3
+        assert ((got - free).abs().max() / free.abs().max()).item() > 5e-2   # the clamp changed the gradients

@@ -102,10 +102,13 @@ def _assert_elementwise(got, ref, bounds, tag, r_lat):
     assert all(v[1] < MAX_REL + r_lat for v in rep.values()), (tag, "max/max", rep)
 
 
-def _assert_exact(got, exact, tag):
-    rep = {k: round(((got[k].double() - exact[k]).abs() / (EXACT_RTOL * exact["abs_" + k] + 1e-30)).max().item(), 3)
+def _assert_exact(got, exact, tag, n_cells=0):
+    # fp32 accumulation (TMEM + split-K folds): the rounding error of a sum of n terms grows like sqrt(n) * 2^-24 of the
+    # sum of |terms|; 1e-5 covers every contraction up to ~1e4 cells, longer ones (dW / db over a whole batch) get the sqrt
+    rtol = EXACT_RTOL * max(1.0, (n_cells / 1.0e4) ** 0.5)
+    rep = {k: round(((got[k].double() - exact[k]).abs() / (rtol * exact["abs_" + k] + 1e-30)).max().item(), 3)
            for k in ("d_enc", "d_dec", "dW", "db")}
-    print(tag, "fp64 GEMM on the decoded images (worst err / (1e-5 sum|terms|)):", rep)
+    print(tag, f"fp64 GEMM on the decoded images (worst err / ({rtol:.1e} sum|terms|)):", rep)
     assert all(v <= 1.0 for v in rep.values()), (tag, "fp64 GEMM on the decoded images", rep)
 
 
@@ -140,12 +143,14 @@ def test_backward_elementwise_vs_reference_and_exact_vs_images(shape, act, eps):
         if pruned.any():  # what pruning drops is negligible in the REFERENCE's gradient
             assert (ref["dlogits"].abs() * pruned[..., None]).max().item() < 1e-7
     m = mask[..., None]
-    err = ((dY - ref["dlogits"]).abs() - DLOGITS_ATOL - (DLOGITS_RTOL + _lattice_floor(ref["costs"], T, U)) * ref["dlogits"].abs()) * m
-    assert err.max().item() <= 0.0, (shape, "dlogits images", ((dY - ref["dlogits"]).abs() * m).max().item())
-    assert torch.equal(J * m, ref["joint"] * m), "J operand images must be the bf16-rounded joint tensor exactly"
+    zero = torch.zeros(())
+    dY, J = torch.where(m, dY, zero), torch.where(m, J, zero)  # tiles the kernels never wrote hold stale bytes (possibly NaN patterns)
+    err = torch.where(m, (dY - ref["dlogits"]).abs() - DLOGITS_ATOL - (DLOGITS_RTOL + _lattice_floor(ref["costs"], T, U)) * ref["dlogits"].abs(), zero)
+    assert err.max().item() <= 0.0, (shape, "dlogits images", torch.where(m, (dY - ref["dlogits"]).abs(), zero).max().item())
+    assert torch.equal(J, torch.where(m, ref["joint"], zero)), "J operand images must be the bf16-rounded joint tensor exactly"
     # (2) the GEMMs / reductions on exactly those operands
     exact = imd.backward_from_operands(dY, J, W.float(), enc.float(), dec.float(), act, 0.01, mask)
-    _assert_exact(got, exact, f"{shape} {act} eps={eps}")
+    _assert_exact(got, exact, f"{shape} {act} eps={eps}", int(mask.sum()))
 
 
 @pytest.mark.timeout(900)
@@ -169,11 +174,13 @@ def test_dlogits_images_ragged_config2_pair_with_pruning():
     assert 0 < int(mask.sum()) < int(live.sum())  # pruning did skip tiles
     assert (ref["dlogits"].abs() * (live & ~mask)[..., None]).max().item() < 1e-7
     m = mask[..., None]
-    err = ((dY - ref["dlogits"]).abs() - DLOGITS_ATOL - (DLOGITS_RTOL + _lattice_floor(ref["costs"], T, U)) * ref["dlogits"].abs()) * m
-    assert err.max().item() <= 0.0, ((dY - ref["dlogits"]).abs() * m).max().item()
+    zero = torch.zeros(())
+    dY, J = torch.where(m, dY, zero), torch.where(m, J, zero)
+    err = torch.where(m, (dY - ref["dlogits"]).abs() - DLOGITS_ATOL - (DLOGITS_RTOL + _lattice_floor(ref["costs"], T, U)) * ref["dlogits"].abs(), zero)
+    assert err.max().item() <= 0.0, torch.where(m, (dY - ref["dlogits"]).abs(), zero).max().item()
     exact = imd.backward_from_operands(dY, J, W.float(), enc.float(), dec.float(), "leaky_relu", 0.01, mask, dtype=torch.float64,
                                        with_bounds=True)
-    _assert_exact(got, exact, "config-2 pair")
+    _assert_exact(got, exact, "config-2 pair", int(mask.sum()))
     bounds = imd.backward_from_operands(ref["dlogits"], ref["joint"], W.float(), enc.float(), dec.float(), "leaky_relu", 0.01, live,
                                         dtype=torch.float32)
     _assert_elementwise(got, ref, bounds, "config-2 pair", _lattice_floor(ref["costs"], T, U))

@@ -189,8 +189,8 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
                     const int32_t* logit_lengths, const int32_t* target_lengths, int B, int T, int U, int H, int V,
                     int blank, int act_kind, float act_param, const float* lat2, const float* logz,
                     const float* alpha, const float* beta, const float* cost, const float* dcost, void* workspace,
-                    size_t workspace_bytes, long long max_chunk_cells, float prune_log2_eps, float* d_enc, float* d_dec,
-                    float* dW, float* db, tsasr_stream_t stream) {
+                    size_t workspace_bytes, long long max_chunk_cells, float prune_log2_eps, float clamp, float* d_enc,
+                    float* d_dec, float* dW, float* db, tsasr_stream_t stream) {
     NvtxRange nvtx_range("tsasr_joint_bwd");
     if (int rc = check_dims(B, T, U, V, blank)) return rc;
     REQUIRE(enc && dec && W && bias && logit_lengths && target_lengths && lat2 && logz && alpha && beta && cost &&
@@ -216,6 +216,7 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
     jp.beta = beta;
     jp.cost = cost;
     jp.dcost = dcost;
+    jp.clamp = clamp;
     jp.dY_img = reinterpret_cast<__nv_bfloat16*>(ws);
     jp.J_img = reinterpret_cast<__nv_bfloat16*>(ws + pl.dY_bytes);
 
@@ -299,7 +300,7 @@ int tsasr_joint_bwd(const void* enc, const void* dec, const void* W, const float
         }
         {
             ScopedTiming tm("joint_gemm_kernel<GRAD>", st);
-            if (int rc = launch_joint<MODE_GRAD>(maps, jp, sms, st)) return rc;
+            if (int rc = clamp > 0.f ? launch_joint<MODE_GRAD_CLAMP>(maps, jp, sms, st) : launch_joint<MODE_GRAD>(maps, jp, sms, st)) return rc;
         }
 
         {

@@ -71,7 +71,12 @@ static constexpr int kWarpMma = 19;       // leader: MMA issue; partner: accumul
 static constexpr float kLog2eF = 1.4426950408889634f;
 static constexpr float kLn2F = 0.6931471805599453f;
 
-enum JointMode : int { MODE_FWD = 0, MODE_GRAD = 1, MODE_DEBUG = 2 };
+enum JointMode : int { MODE_FWD = 0, MODE_GRAD = 1, MODE_DEBUG = 2, MODE_GRAD_CLAMP = 3 };
+// MODE_GRAD_CLAMP: MODE_GRAD with torchaudio's `clamp` (rnnt_loss(clamp=c)): the gradient of the UNIT cost is clamped
+// to [-c, c] and multiplied by the upstream factor dcost[b] afterwards (ComputeGradients, then `grad * dy`,
+// torchaudio/functional/functional.py:1729-1734).  A separate instantiation, so the default path pays nothing.
+template <int MODE>
+struct ModeTraits { static constexpr bool grad = MODE == MODE_GRAD || MODE == MODE_GRAD_CLAMP; static constexpr bool clamp = MODE == MODE_GRAD_CLAMP; };
 
 struct JointParams {
     const float* bias;          // [V]
@@ -102,6 +107,7 @@ struct JointParams {
     const float* beta;
     const float* cost;
     const float* dcost;
+    float clamp;                // MODE_GRAD_CLAMP: bound on the unit-cost gradient (> 0)
     __nv_bfloat16* dY_img;      // [tile - tile_begin][NT*4][128 x 64] SWIZZLE_128B images
     __nv_bfloat16* J_img;       // [tile - tile_begin][KB][128 x 64] SWIZZLE_128B images
     // MODE_DEBUG output
@@ -268,7 +274,7 @@ __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a,
             for (int i = 0; i < 4; ++i) {
                 const uint32_t off = sw128_offset((uint32_t)(rg + 32 * i), (uint32_t)c);
                 *reinterpret_cast<uint4*>(blk + off) = o[i];
-                if (MODE == MODE_GRAD) {
+                if (ModeTraits<MODE>::grad) {
                     uint8_t* img = reinterpret_cast<uint8_t*>(p.J_img) + ((size_t)(tile - p.tile_begin) * KB + kb) * kABlockBytes;
                     *reinterpret_cast<uint4*>(img + off) = o[i];
                 }
@@ -555,9 +561,11 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
             // per-row state
             float run_m = -INFINITY, run_s = 0.f, y_blank = -INFINITY, y_label = -INFINITY;  // MODE_FWD (log2 domain)
             float nz2 = 0.f, occ = 0.f, ob = 0.f, oe = 0.f, p_blank = 0.f, p_label = 0.f;    // MODE_GRAD
-            if (MODE == MODE_GRAD && valid) {
+            float dy_post = 1.f;  // MODE_GRAD_CLAMP: upstream factor applied AFTER the clamp (occ / ob / oe are unit-cost terms then)
+            if (ModeTraits<MODE>::grad && valid) {
                 const float Lp = -p.cost[tc.b];
-                const float dy = p.dcost ? p.dcost[tc.b] : 1.f;
+                float dy = p.dcost ? p.dcost[tc.b] : 1.f;
+                if (ModeTraits<MODE>::clamp) { dy_post = dy; dy = 1.f; }
                 const float a = p.alpha[cell_o];
                 const float2 lp = p.lat2_in[cell_o];
                 occ = dy * __expf(a + p.beta[cell_o] - Lp);
@@ -608,9 +616,9 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                 // chunks (16 columns each) of this group's half tile that need the rare path of process(): bit i <-> cc = c_begin + 16 i
                 uint32_t special_mask = 0;
                 uint8_t* img_grp = nullptr;  // MODE_GRAD: first dY image of this group's half tile
-                if (MODE == MODE_GRAD)
+                if (ModeTraits<MODE>::grad)
                     img_grp = reinterpret_cast<uint8_t*>(p.dY_img) + ((size_t)(tile - p.tile_begin) * (NT * 4) + vt * 4 + grp * 2) * kABlockBytes;
-                if (MODE == MODE_FWD || MODE == MODE_GRAD) {
+                if (MODE == MODE_FWD || ModeTraits<MODE>::grad) {
                     const int g0 = vt * kTileN + c_begin;  // first vocabulary column of this group's half tile
                     if ((unsigned)(p.blank - g0) < (unsigned)kGrpCols) special_mask |= 1u << ((p.blank - g0) >> 4);
 #pragma unroll
@@ -690,7 +698,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                         const float2 s2 = fadd2(s4a, s4b);
                         run_s = fmaf(run_s, ex2_approx(run_m - mn), s2.x + s2.y);
                         run_m = mn;
-                    } else if (MODE == MODE_GRAD) {
+                    } else if (ModeTraits<MODE>::grad) {
                         // dlogits = occ * softmax - [blank] ob - [label] oe, emitted as bf16 into the
                         // [128 x 64] SWIZZLE_128B image of this (tile, 64-column block)
                         uint32_t packed[8];
@@ -698,7 +706,10 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj) {
                             const float2 d = fadd2(y2[jj], nz);
-                            const float2 g = fmul2(make_float2(ex2_approx(d.x), ex2_approx(d.y)), oc);
+                            float2 g = fmul2(make_float2(ex2_approx(d.x), ex2_approx(d.y)), oc);
+                            if (ModeTraits<MODE>::clamp) {  // occ * p >= 0: only the upper bound can bite; then the upstream factor
+                                g = fmul2(make_float2(fminf(g.x, p.clamp), fminf(g.y, p.clamp)), make_float2(dy_post, dy_post));
+                            }
                             packed[jj] = pack_bf16x2(g.x, g.y);
                         }
                         if (special && col0 + 16 > p.V) {  // end of the vocabulary: padded columns are exact zeros
@@ -725,13 +736,15 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                             if (p.blank >= col0 && p.blank < col0 + 16) {
                                 float g = occ * p_blank - ob;
                                 if (label == p.blank) g -= oe;
+                                if (ModeTraits<MODE>::clamp) g = fminf(fmaxf(g, -p.clamp), p.clamp) * dy_post;
                                 const int cv = p.blank & 63;
                                 rowp[(sw128_offset((uint32_t)row, (uint32_t)(cv >> 3)) >> 1) + (cv & 7)] = __float2bfloat16_rn(g);
                             }
                             if (label >= col0 && label < col0 + 16 && label != p.blank) {
+                                float g = occ * p_label - oe;
+                                if (ModeTraits<MODE>::clamp) g = fminf(fmaxf(g, -p.clamp), p.clamp) * dy_post;
                                 const int cv = label & 63;
-                                rowp[(sw128_offset((uint32_t)row, (uint32_t)(cv >> 3)) >> 1) + (cv & 7)] =
-                                    __float2bfloat16_rn(occ * p_label - oe);
+                                rowp[(sw128_offset((uint32_t)row, (uint32_t)(cv >> 3)) >> 1) + (cv & 7)] = __float2bfloat16_rn(g);
                             }
                         }
                     } else {  // MODE_DEBUG
@@ -762,7 +775,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                         if (!abl_nomath) process(raw1, ci + 1);
                     }
                 }
-                if (MODE == MODE_GRAD && n_all < kTileN) {
+                if (ModeTraits<MODE>::grad && n_all < kTileN) {
                     // zero-fill the 16-column chunks of the last tile the MMA did not produce, so the
                     // backward GEMMs read finite zeros for the padded vocabulary columns
                     const int cols_pad = min(((p.V + 63) / 64) * 64 - vt * kTileN, c_begin + kGrpCols);  // columns the images cover

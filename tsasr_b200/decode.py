@@ -107,10 +107,76 @@ def fused_joint_forward_step(tjoint, classifier_network, softmax):
     return step
 
 
-def patch_searcher(searcher):
-    """Replace ``searcher._joint_forward_step`` by the fused step (returns True when patched)."""
+_RECURRENT = ("RNN", "LSTM", "GRU", "LiGRU", "LiGRU_Layer")
+
+
+def _forward_pn(tokens, layers, hidden=None):
+    """``TransducerBeamSearcher._forward_PN`` (SB/decoders/transducer.py:468-502): recurrent layers are recognised by
+    their class NAME and take / return the hidden state."""
+    out = tokens
+    for layer in layers:
+        if layer.__class__.__name__ in _RECURRENT:
+            out, hidden = layer(out, hidden)
+        else:
+            out = layer(out)
+    return out, hidden
+
+
+def _select_hidden(mask_b, new, old):
+    """Per-utterance choice between the freshly computed and the kept hidden state ([layers, B, hidden] tensors, or the
+    (h, c) tuple of an LSTM) -- the device-side form of ``_update_hiddens`` (transducer.py:443-466)."""
+    if isinstance(old, tuple):
+        return tuple(_select_hidden(mask_b, n, o) for n, o in zip(new, old))
+    return torch.where(mask_b.view(1, -1, 1), new, old)
+
+
+def greedy_decode_on_device(tn_output, decode_network_lst, joint_step, blank_id=0):
+    """``TransducerBeamSearcher.transducer_greedy_decode`` (SB/decoders/transducer.py:138-218) with the hypothesis
+    bookkeeping on the device: no host synchronisation inside the frame loop.
+
+    The reference reads ``positions[i].item()`` for every utterance of every frame (B x T device->host syncs) and runs
+    the prediction network on the utterances that emitted a label.  Here the frame loop only queues work: the arg-max,
+    the "emitted a non-blank label" mask, the running scores and the [B, T] table of emitted labels stay on the device;
+    the prediction network steps ALL utterances and a masked select keeps the old output / hidden state of those that
+    emitted blank (rows of a recurrent step are independent, so the kept rows are exactly what the reference keeps).
+    ONE device->host copy at the end turns the table into the reference's lists.
+
+    Returns the reference's 4-tuple: (list of label lists, mean of exp(summed log-probs) as a CPU tensor, None, None)."""
+    B, T = tn_output.shape[0], tn_output.shape[1]
+    dev = tn_output.device
+    with torch.no_grad():
+        input_pn = torch.full((B, 1), int(blank_id), device=dev, dtype=torch.int32)
+        out_pn, hidden = _forward_pn(input_pn, decode_network_lst)                     # transducer.py:172-173
+        emitted = torch.empty((T, B), device=dev, dtype=torch.int64)
+        scores = torch.zeros((B,), device=dev, dtype=torch.float32)
+        for t in range(T):
+            log_probs = joint_step(tn_output[:, t, :].unsqueeze(1).unsqueeze(1), out_pn.unsqueeze(1))
+            logp, pos = torch.max(log_probs.reshape(B, -1), dim=1)                    # :181-184 (log-softmax is idempotent)
+            emit = pos != blank_id                                                    # :189-194
+            emitted[t] = pos
+            scores = scores + torch.where(emit, logp.to(torch.float32), torch.zeros_like(scores))
+            input_pn = torch.where(emit.view(B, 1), pos.to(input_pn.dtype).view(B, 1), input_pn)
+            new_out, new_hidden = _forward_pn(input_pn, decode_network_lst, hidden)   # :195-207, all rows
+            out_pn = torch.where(emit.view(B, 1, 1), new_out, out_pn)                 # :208-212, rows that emitted
+            hidden = _select_hidden(emit, new_hidden, hidden) if hidden is not None else new_hidden
+        table = emitted.t().cpu()                                                     # the only device->host copy
+        score = scores.exp().mean().cpu()
+    hyps = [[int(x) for x in row[row != blank_id].tolist()] for row in table]
+    return hyps, score, None, None
+
+
+def patch_searcher(searcher, on_device_greedy=False):
+    """Replace ``searcher._joint_forward_step`` by the fused step (returns True when patched).
+    ``on_device_greedy``: additionally replace the greedy searcher (``beam_size <= 1``) by ``greedy_decode_on_device``
+    -- same hypotheses and score, no per-frame host synchronisation."""
     step = fused_joint_forward_step(searcher.tjoint, searcher.classifier_network, searcher.softmax)
     if step is None:
         return False
     searcher._joint_forward_step = types.MethodType(lambda self, h_i, out_PN: step(h_i, out_PN), searcher)
+    if on_device_greedy and getattr(searcher, "beam_size", 2) <= 1:
+        def greedy(self, tn_output):
+            return greedy_decode_on_device(tn_output, self.decode_network_lst, self._joint_forward_step, self.blank_id)
+
+        searcher.transducer_greedy_decode = types.MethodType(greedy, searcher)
+        searcher.searcher = searcher.transducer_greedy_decode
     return True

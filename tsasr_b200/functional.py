@@ -238,7 +238,7 @@ class FusedJointRnnt(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, dec, W, bias, targets, logit_lengths, target_lengths, blank, act_kind, act_param,
-                max_chunk_cells, prune_log2_eps=None):
+                max_chunk_cells, prune_log2_eps=None, clamp=-1.0):
         H = enc.shape[-1]
         enc_, dec_, W_ = enc.detach(), dec.detach(), W.detach()
         if H % 64:  # the kernels contract over whole 64-wide k-blocks: zero columns add nothing (act(0) = 0 for every
@@ -251,7 +251,7 @@ class FusedJointRnnt(torch.autograd.Function):
         lat2, logz = ops.joint_fwd(enc16, dec16, W16, b32, targets, logit_lengths, target_lengths, blank, act_kind, act_param)
         alpha, beta, cost, _, _ = ops.alpha_beta(lat2, logit_lengths, target_lengths, B, T, U)
         ctx.save_for_backward(enc16, dec16, W16, b32, targets, logit_lengths, target_lengths, lat2, logz, alpha, beta, cost)
-        ctx.cfg = (blank, act_kind, act_param, max_chunk_cells, prune_log2_eps)
+        ctx.cfg = (blank, act_kind, act_param, max_chunk_cells, prune_log2_eps, clamp)
         ctx.in_dtypes = (enc.dtype, dec.dtype, W.dtype, bias.dtype)
         ctx.H = H
         return cost
@@ -259,14 +259,14 @@ class FusedJointRnnt(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dcost):
         enc16, dec16, W16, b32, targets, ll, tl, lat2, logz, alpha, beta, cost = ctx.saved_tensors
-        blank, act_kind, act_param, max_chunk_cells, prune_log2_eps = ctx.cfg
+        blank, act_kind, act_param, max_chunk_cells, prune_log2_eps, clamp = ctx.cfg
         dcost = dcost.to(torch.float32).contiguous()
         d_enc, d_dec, dW, db = ops.joint_bwd(enc16, dec16, W16, b32, targets, ll, tl, blank, act_kind, act_param,
-                                             lat2, logz, alpha, beta, cost, dcost, max_chunk_cells, prune_log2_eps)
+                                             lat2, logz, alpha, beta, cost, dcost, max_chunk_cells, prune_log2_eps, clamp)
         de, dd, dw, dbt = ctx.in_dtypes
         if d_enc.shape[-1] != ctx.H:  # drop the gradients of the zero padding
             d_enc, d_dec, dW = d_enc[..., :ctx.H].contiguous(), d_dec[..., :ctx.H].contiguous(), dW[:, :ctx.H].contiguous()
-        return (d_enc.to(de), d_dec.to(dd), dW.to(dw), db.to(dbt), None, None, None, None, None, None, None, None)
+        return (d_enc.to(de), d_dec.to(dd), dW.to(dw), db.to(dbt), None, None, None, None, None, None, None, None, None)
 
 
 class _NumbaReduce(torch.autograd.Function):
@@ -295,11 +295,13 @@ class _NumbaReduce(torch.autograd.Function):
 
 def fused_joint_rnnt_loss(enc_out, dec_out, weight, bias, targets, logit_lengths, target_lengths, blank=0,
                           activation="leaky_relu", act_param=0.01, reduction="mean", check_lengths=True,
-                          max_chunk_cells=0, relative_lengths=False, prune_log2_eps=None, numba_semantics=False):
+                          max_chunk_cells=0, relative_lengths=False, prune_log2_eps=None, numba_semantics=False, clamp=-1.0):
     """Functional form of the fused path.  Lengths are absolute int32 counts, or -- with ``relative_lengths=True`` --
     SpeechBrain's relative floats, converted bit-exactly like SB/nnet/losses.py:58-59.
     ``prune_log2_eps``: backward tile pruning threshold (None: TSASR_PRUNE_LOG2_EPS or -30; >= 0: off), see
     include/tsasr_b200.h.
+    ``clamp`` > 0: torchaudio's ``rnnt_loss(clamp=...)``: dlogits of the unit cost clamped to [-clamp, clamp] inside the
+    gradient pass, before the upstream factor (1/B under "mean") multiplies them.
     ``numba_semantics``: value and gradient scale of the reference's Numba branch (``use_torchaudio=False`` /
     ``TransducerLoss``): ``reduce_b(-log P_b / T_b)``, gradient of ``sum_b -log P_b`` times the incoming grad_output."""
     if not numba_semantics:
@@ -325,7 +327,7 @@ def fused_joint_rnnt_loss(enc_out, dec_out, weight, bias, targets, logit_lengths
         logit_lengths, target_lengths, stats, ready = _prepare_lengths(logit_lengths, target_lengths, T, targets.shape[1],
                                                                        relative_lengths)
         costs = FusedJointRnnt.apply(enc_out, dec_out, weight, bias, targets, logit_lengths, target_lengths, int(blank),
-                                     _lib.ACT_CODES[activation], float(act_param), int(max_chunk_cells), prune_log2_eps)
+                                     _lib.ACT_CODES[activation], float(act_param), int(max_chunk_cells), prune_log2_eps, float(clamp))
         if check_lengths:
             # raises what torchaudio raises; the kernels above are already queued
             _DeferredLengthCheck(stats, ready).finish(T, U, targets.shape[1])

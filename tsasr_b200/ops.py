@@ -178,8 +178,9 @@ def last_backward_tile_stats(dev=None):
 
 
 def joint_bwd(enc, dec, W, bias, targets, logit_lengths, target_lengths, blank, act_kind, act_param,
-              lat2, logz, alpha, beta, cost, dcost, max_chunk_cells=0, prune_log2_eps=None):
-    """Backward of the fused chain -> (d_enc [B,T,H], d_dec [B,U,H], dW [V,H], db [V]) fp32."""
+              lat2, logz, alpha, beta, cost, dcost, max_chunk_cells=0, prune_log2_eps=None, clamp=-1.0):
+    """Backward of the fused chain -> (d_enc [B,T,H], d_dec [B,U,H], dW [V,H], db [V]) fp32.
+    ``clamp`` > 0: torchaudio's gradient clamp on the dlogits of the unit cost (see include/tsasr_b200.h)."""
     dev = _require_cuda(enc, dec, W, bias, lat2, logz, alpha, beta, cost, dcost)
     B, T, H = enc.shape
     U = dec.shape[1]
@@ -198,7 +199,7 @@ def joint_bwd(enc, dec, W, bias, targets, logit_lengths, target_lengths, blank, 
         _lib.check(lib.tsasr_joint_bwd(
             _p(enc), _p(dec), _p(W), _p(bias), _p(targets), _p(logit_lengths), _p(target_lengths),
             B, T, U, H, V, int(blank), int(act_kind), float(act_param), _p(lat2), _p(logz), _p(alpha), _p(beta),
-            _p(cost), _p(dcost), _p(ws), ctypes.c_size_t(ws.numel()), int(max_chunk_cells), float(prune_log2_eps),
+            _p(cost), _p(dcost), _p(ws), ctypes.c_size_t(ws.numel()), int(max_chunk_cells), float(prune_log2_eps), float(clamp),
             _p(d_enc), _p(d_dec), _p(dW), _p(db), _stream(dev)))
     return d_enc, d_dec, dW, db
 
