@@ -98,6 +98,27 @@ int tsasr_joint_fwd(const void* enc, const void* dec, const void* W, const float
                     const int32_t* logit_lengths, const int32_t* target_lengths, int B, int T, int U, int H, int V,
                     int blank, int act_kind, float act_param, float* lat2, float* logz, tsasr_stream_t stream);
 
+/* The whole forward of the fused loss behind ONE call: input preparation (bf16 operand copies when the operands are
+ * fp32, int64 -> int32 targets as SB/nnet/losses.py:74 casts them, the length conversion of SB/nnet/losses.py:58-59 and
+ * the statistics of tsasr_prepare_lengths -- one launch), tsasr_joint_fwd and tsasr_lattice_alpha_beta, queued back to
+ * back on `stream` (what train_librispeechmix_scratch.py:132,135,158 + torchaudio's forward amount to).
+ *   operand_dtype: TSASR_F32 (enc, dec, W are fp32 and converted into scratch) or TSASR_BF16 (used as they are);
+ *   targets: int32 [B,U-1], or int64 when targets_i64 != 0;  lengths: rel_* fp32 (SpeechBrain relative) or abs_* int32;
+ *   scratch: 256-byte aligned, tsasr_joint_loss_fwd_layout() gives the byte offsets
+ *     {enc16, dec16, W16, targets32, logit_lengths, target_lengths, stats[4], total}; the int32 lengths, the statistics
+ *     and -- where a conversion happened -- the bf16 operands / int32 targets live there and feed tsasr_joint_bwd;
+ *   stats_host (may be NULL): HOST pointer to 8 int32 of mapped pinned memory (cudaHostAlloc / torch pin_memory); the
+ *     preparation kernel writes {max T_b, max labels, min T_b, min labels} there, a system-scope fence, then
+ *     stats_host[4] = stats_seq -- the caller polls the tag and performs torchaudio's argument checks without a stream,
+ *     event or copy of its own (the kernels clamp every length, so nothing depends on the outcome);
+ *   cost3: 3*B floats {cost[b] = -log P, ll_alpha[b], ll_beta[b]}. */
+int tsasr_joint_loss_fwd_layout(int B, int T, int U, int H, int V, size_t* offsets8);
+int tsasr_joint_loss_fwd(const void* enc, const void* dec, const void* W, int operand_dtype, const float* bias, const void* targets,
+                         int targets_i64, const float* rel_logit_lengths, const float* rel_target_lengths,
+                         const int32_t* abs_logit_lengths, const int32_t* abs_target_lengths, int B, int T, int U, int H, int V,
+                         int blank, int act_kind, float act_param, void* scratch, size_t scratch_bytes, int32_t* stats_host,
+                         int stats_seq, float* lat2, float* logz, float* alpha, float* beta, float* cost3, tsasr_stream_t stream);
+
 /* Workspace (bytes) tsasr_joint_bwd needs; bounded independently of B*T*U by `max_chunk_cells`
  * (0 = library default). */
 size_t tsasr_joint_bwd_workspace_bytes(int B, int T, int U, int H, int V, long long max_chunk_cells);

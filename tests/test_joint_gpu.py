@@ -317,6 +317,41 @@ def test_relative_length_conversion_kernel_is_bit_exact():
         assert torch.equal(ll2.cpu(), want_l) and stats2.cpu().tolist() == stats.cpu().tolist()
 
 
+def test_single_call_forward_converts_lengths_and_targets_bit_exactly():
+    """tsasr_joint_loss_fwd (the whole forward behind one C call): its preparation kernel must produce exactly the
+    integers of SB/nnet/losses.py:58-59 (fp32 product, round-half-to-even, int32) and of ``targets.int()`` (:74), on
+    half-way cases, for thousands of utterances at once."""
+    from tsasr_b200.functional import FusedJointRnnt
+
+    d = _dev()
+    g = torch.Generator().manual_seed(1)
+    for T, U in ((37, 7), (400, 3)):
+        n_tg = U - 1
+        halves = torch.arange(1, 2 * T + 1, dtype=torch.float32) / (2.0 * T)           # k / 2T: exact .5 products
+        rel_l = torch.cat([halves, torch.rand(1500, generator=g).clamp(min=0.02), torch.tensor([1.0, 0.99999994])])
+        B = rel_l.shape[0]
+        rel_t = torch.rand(B, generator=g)
+        rel_t[: 2 * n_tg + 1] = torch.arange(0, 2 * n_tg + 1, dtype=torch.float32) / (2.0 * n_tg)
+        want_l, want_t = (rel_l * T).round().int(), (rel_t * n_tg).round().int()
+        H, V = 64, 5
+        enc = torch.zeros(B, T, H, device=d)
+        dec = torch.zeros(B, U, H, device=d)
+        W = torch.zeros(V, H, device=d)
+        bias = torch.zeros(V, device=d)
+        targets = torch.randint(1, V, (B, n_tg), generator=g)                           # int64, as the recipe's tokens
+        cost, ll, tl = FusedJointRnnt.apply(enc, dec, W, bias, targets.to(d), rel_l.to(d), rel_t.to(d), True, 0, 0, 0.01, 0, None, -1.0,
+                                            False)
+        torch.cuda.synchronize()
+        assert torch.equal(ll.cpu(), want_l) and torch.equal(tl.cpu(), want_t)
+        assert torch.isfinite(cost).all()
+        # uniform logits: -log P is the number of lattice paths times V^-(steps) -- compare one utterance with the closed form
+        b0 = int(torch.argmax(want_l.long() * 1000 + want_t.long()))
+        Tb, Lb = int(want_l[b0]), int(want_t[b0])
+        import math
+        want = (Tb + Lb) * math.log(V) - math.log(math.comb(Tb - 1 + Lb, Lb))
+        assert abs(cost[b0].item() - want) < 1e-4 * want
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_half_precision_operands_need_no_cast_and_return_their_dtype(dtype):
     """SURVEY 8f N1 (projections as producers): when encoder_proj / decoder_proj already emit bf16 (autocast), enc_out and

@@ -27,6 +27,9 @@ SIGNATURES = {
     "tsasr_logits_grad": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp]),
     "tsasr_logprobs_grad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsasr_joint_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "tsasr_joint_loss_fwd_layout": (_i, [_i, _i, _i, _i, _i, _vp]),
+    "tsasr_joint_loss_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _sz,
+                                  _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsasr_joint_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _ll]),
     "tsasr_joint_bwd_stats_offset": (_sz, [_i, _i, _i, _i, _i, _ll]),
     "tsasr_joint_bwd": (_i, [_vp] * 7 + [_i] * 7 + [_f] + [_vp] * 7 + [_sz, _ll, _f, _f] + [_vp] * 5),

@@ -34,6 +34,9 @@ cudaError_t launch_logprobs_grad(const int*, const int*, const int*, int, int, i
 // prep.cu
 cudaError_t launch_lengths(const float*, const float*, const int*, const int*, int, int, int, int*, int*, int*, cudaStream_t);
 cudaError_t launch_cast3(const float*, size_t, const float*, size_t, const float*, size_t, void*, void*, void*, int, cudaStream_t);
+cudaError_t launch_prepare_inputs(const float*, size_t, const float*, size_t, const float*, size_t, void*, void*, void*, const long long*,
+                                  size_t, int*, const float*, const float*, const int*, const int*, int, int, int, int*, int*, int*, int*,
+                                  int, int, cudaStream_t);
 // decode.cu
 cudaError_t launch_joint_decode_step(const float*, const float*, long long, long long, const float*, const float*, int, int, int,
                                      int, float, float*, void*, cudaStream_t);
@@ -430,6 +433,93 @@ int tsasr_joint_fwd(const void* enc, const void* dec, const void* W, const float
     if (int rc = make_joint_maps(&maps, p, enc, dec, W)) return rc;
     ScopedTiming tm("joint_gemm_kernel<FWD>", static_cast<cudaStream_t>(stream));
     return launch_joint<MODE_FWD>(maps, p, sms, static_cast<cudaStream_t>(stream));
+}
+
+// ---- the whole forward of the fused loss behind ONE call (host-path saver: five launches, no Python in between) ----
+// scratch layout (byte offsets, every block 256-byte aligned): enc16 | dec16 | W16 | targets32 | ll | tl | stats[4]
+static void fwd_scratch_layout(int B, int T, int U, int H, int V, size_t off[8]) {
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    off[0] = 0;
+    off[1] = off[0] + up((size_t)B * T * H * 2);
+    off[2] = off[1] + up((size_t)B * U * H * 2);
+    off[3] = off[2] + up((size_t)V * H * 2);
+    off[4] = off[3] + up((size_t)B * (U > 1 ? U - 1 : 1) * 4);
+    off[5] = off[4] + up((size_t)B * 4);
+    off[6] = off[5] + up((size_t)B * 4);
+    off[7] = off[6] + 256;  // total
+}
+
+int tsasr_joint_loss_fwd_layout(int B, int T, int U, int H, int V, size_t* offsets8) {
+    REQUIRE(offsets8 && B >= 1 && T >= 1 && U >= 1 && H >= 1 && V >= 1, "bad argument");
+    fwd_scratch_layout(B, T, U, H, V, offsets8);
+    return TSASR_OK;
+}
+
+int tsasr_joint_loss_fwd(const void* enc, const void* dec, const void* W, int operand_dtype, const float* bias, const void* targets,
+                         int targets_i64, const float* rel_logit_lengths, const float* rel_target_lengths,
+                         const int32_t* abs_logit_lengths, const int32_t* abs_target_lengths, int B, int T, int U, int H, int V,
+                         int blank, int act_kind, float act_param, void* scratch, size_t scratch_bytes, int32_t* stats_host,
+                         int stats_seq, float* lat2, float* logz, float* alpha, float* beta, float* cost3, tsasr_stream_t stream) {
+    NvtxRange nvtx_range("tsasr_joint_loss_fwd");
+    if (int rc = check_dims(B, T, U, V, blank)) return rc;
+    REQUIRE(enc && dec && W && bias && scratch && lat2 && logz && alpha && beta && cost3, "null pointer argument");
+    REQUIRE(U == 1 || targets, "targets must not be null when U > 1");
+    REQUIRE(operand_dtype == TSASR_F32 || operand_dtype == TSASR_BF16, "operands must be fp32 (converted here) or bf16 (used as they are)");
+    REQUIRE((rel_logit_lengths || abs_logit_lengths) && (rel_target_lengths || abs_target_lengths), "null length argument");
+    REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "scratch must be 256-byte aligned");
+    if (U > 1024) return fail(TSASR_E_UNSUPPORTED, "lattice width U=%d > 1024 is not supported", U);
+    size_t off[8];
+    fwd_scratch_layout(B, T, U, H, V, off);
+    if (scratch_bytes < off[7]) return fail(TSASR_E_WORKSPACE, "scratch too small: need %zu bytes, got %zu", off[7], scratch_bytes);
+    int sms, max_smem;
+    if (int rc = device_info(&sms, &max_smem)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t* sc = static_cast<uint8_t*>(scratch);
+    const bool cast = operand_dtype == TSASR_F32;
+    const void* enc16 = cast ? sc + off[0] : enc;
+    const void* dec16 = cast ? sc + off[1] : dec;
+    const void* W16 = cast ? sc + off[2] : W;
+    const int32_t* tg32 = targets_i64 ? reinterpret_cast<const int32_t*>(sc + off[3]) : static_cast<const int32_t*>(targets);
+    int32_t* ll = reinterpret_cast<int32_t*>(sc + off[4]);
+    int32_t* tl = reinterpret_cast<int32_t*>(sc + off[5]);
+    int32_t* stats = reinterpret_cast<int32_t*>(sc + off[6]);
+    if (cast) {
+        REQUIRE(((size_t)B * T * H) % 4 == 0 && ((size_t)B * U * H) % 4 == 0 && ((size_t)V * H) % 4 == 0, "operand element counts must be multiples of 4");
+        REQUIRE(((reinterpret_cast<uintptr_t>(enc) | reinterpret_cast<uintptr_t>(dec) | reinterpret_cast<uintptr_t>(W)) & 15) == 0,
+                "fp32 operands must be 16-byte aligned");
+    }
+    int32_t* stats_dev = nullptr;  // device-side address of the caller's mapped pinned landing slot (or none)
+    if (stats_host) {
+        void* dptr = nullptr;
+        cudaError_t e = cudaHostGetDevicePointer(&dptr, stats_host, 0);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(TSASR_E_INVALID, "stats_host is not mapped pinned host memory: %s", cudaGetErrorString(e)); }
+        stats_dev = static_cast<int32_t*>(dptr);
+    }
+    JointParams p;
+    if (int rc = fill_joint_params(p, enc16, dec16, bias, tg32, ll, tl, B, T, U, H, V, blank, act_kind, act_param, max_smem)) return rc;
+    {
+        ScopedTiming tm("prepare_inputs_kernel", st);
+        cudaError_t e = launch_prepare_inputs(
+            cast ? static_cast<const float*>(enc) : nullptr, cast ? (size_t)B * T * H : 0, cast ? static_cast<const float*>(dec) : nullptr,
+            cast ? (size_t)B * U * H : 0, cast ? static_cast<const float*>(W) : nullptr, cast ? (size_t)V * H : 0, sc + off[0], sc + off[1],
+            sc + off[2], targets_i64 ? static_cast<const long long*>(targets) : nullptr, (size_t)B * (U - 1),
+            reinterpret_cast<int*>(sc + off[3]), rel_logit_lengths, rel_target_lengths, abs_logit_lengths, abs_target_lengths, B, T, U - 1,
+            ll, tl, stats, stats_dev, stats_seq, sms, st);
+        ++g_launches;
+        if (e != cudaSuccess) return cuda_fail(e, "prepare_inputs_kernel");
+    }
+    p.lat2 = reinterpret_cast<float2*>(lat2);
+    p.logz = logz;
+    JointMaps maps;
+    if (int rc = make_joint_maps(&maps, p, enc16, dec16, W16)) return rc;
+    {
+        ScopedTiming tm("joint_gemm_kernel<FWD>", st);
+        if (int rc = launch_joint<MODE_FWD>(maps, p, sms, st)) return rc;
+    }
+    ScopedTiming tm("alpha_beta_kernel", st);
+    cudaError_t e = launch_alpha_beta(reinterpret_cast<const float2*>(lat2), ll, tl, B, T, U, alpha, beta, cost3 + B, cost3 + 2 * B, cost3, st);
+    g_launches += 2;
+    return e == cudaSuccess ? TSASR_OK : cuda_fail(e, "alpha_beta_kernel");
 }
 
 int tsasr_prepare_lengths(const float* rel_logit_lengths, const float* rel_target_lengths, const int32_t* abs_logit_lengths,

@@ -5,6 +5,7 @@ vendor/speechbrain/speechbrain/nnet/losses.py:72-79 -- in signature, semantics a
 (same exception types for the same precondition violations).
 """
 import threading
+import time
 
 import torch
 
@@ -228,36 +229,159 @@ def _operands_bf16(enc, dec, W):
     return tuple(t.to(torch.bfloat16).contiguous() for t in ts)
 
 
+class _StatsRing:
+    """Landing slots (mapped pinned host memory) for the length statistics of the fused forward: the preparation kernel
+    writes {max T_b, max labels, min T_b, min labels}, fences, then writes a sequence tag; the host polls the tag.  No
+    stream, event or copy is involved, so torchaudio's argument checks cost a few microseconds of host time.  One ring per
+    (thread, device); 64 slots, so a check may lag many calls behind without being overwritten."""
+
+    _tls = threading.local()
+    SLOTS = 64
+
+    def __init__(self):
+        self.buf = torch.zeros((self.SLOTS, 8), dtype=torch.int32).pin_memory()
+        self.view = self.buf.numpy()
+        self.seq = 0
+
+    @classmethod
+    def get(cls, dev):
+        rings = cls._tls.__dict__.setdefault("rings", {})
+        ring = rings.get(dev)
+        if ring is None:
+            ring = rings[dev] = cls()
+        return ring
+
+    def next_slot(self):
+        self.seq = self.seq % 0x3FFFFFFF + 1
+        slot = self.seq % self.SLOTS
+        self.view[slot, 4] = 0
+        return slot, self.seq, self.buf.data_ptr() + 32 * slot
+
+    def wait(self, slot, seq, dev):
+        """-> (max T_b, max labels, min T_b, min labels) once the kernel has delivered them."""
+        row = self.view[slot]
+        if row[4] != seq:
+            deadline = time.perf_counter() + 20.0
+            while row[4] != seq:
+                if time.perf_counter() > deadline:  # never expected: fall back to a full synchronisation
+                    torch.cuda.current_stream(dev).synchronize()
+                    if row[4] != seq:
+                        raise RuntimeError("tsasr_b200: the length statistics of the fused forward never arrived")
+        return int(row[0]), int(row[1]), int(row[2]), int(row[3])
+
+
+_layout_cache = {}
+
+
+def _fwd_layout(B, T, U, H, V):
+    key = (B, T, U, H, V)
+    off = _layout_cache.get(key)
+    if off is None:
+        import ctypes
+
+        arr = (ctypes.c_size_t * 8)()
+        _lib.check(_lib.load().tsasr_joint_loss_fwd_layout(B, T, U, H, V, ctypes.cast(arr, ctypes.c_void_p)))
+        off = _layout_cache[key] = tuple(int(x) for x in arr)
+    return off
+
+
+def _raise_length_errors(stats, T, U, n_targets):
+    max_t, max_l, min_t, min_l = stats
+    if max_t != T:
+        raise RuntimeError("input length mismatch")
+    if max_l + 1 != U:
+        raise RuntimeError("output length mismatch")
+    if n_targets != max_l:
+        raise RuntimeError("target length mismatch")
+    if min_t < 1 or min_l < 0:
+        raise RuntimeError("logit_lengths must be >= 1 and target_lengths >= 0")
+
+
 class FusedJointRnnt(torch.autograd.Function):
     """costs[b] of joint("sum") + activation + head Linear + RNN-T loss without the 4-D tensors.
 
     Differentiable inputs: enc_out [B,T,H], dec_out [B,U,H], W [V,H], bias [V]
     (train_librispeechmix_scratch.py:122,127,135).  Operands are rounded to bf16 once on entry; all
     accumulation is fp32 (TMEM), the lattice is fp32.
+
+    The whole forward -- input preparation (bf16 operand copies, int32 targets, the integer length conversion of
+    SB/nnet/losses.py:58-59 with its statistics), the joint GEMM with its online log-softmax and the alpha/beta DP -- is ONE
+    call into the library (``tsasr_joint_loss_fwd``): the host time in front of the first GEMM launch is GPU idle time in
+    a training loop that reads its loss every step (SB/core.py:1096).
+    Returns (costs [B], int32 logit_lengths [B], int32 target_lengths [B]); only the first output is differentiable.
     """
 
     @staticmethod
-    def forward(ctx, enc, dec, W, bias, targets, logit_lengths, target_lengths, blank, act_kind, act_param,
-                max_chunk_cells, prune_log2_eps=None, clamp=-1.0):
-        H = enc.shape[-1]
-        enc_, dec_, W_ = enc.detach(), dec.detach(), W.detach()
-        if H % 64:  # the kernels contract over whole 64-wide k-blocks: zero columns add nothing (act(0) = 0 for every
-            pad = (0, 64 - H % 64)  # fused activation, and the padded W columns are zero anyway)
-            enc_, dec_, W_ = (torch.nn.functional.pad(t, pad) for t in (enc_, dec_, W_))
-        enc16, dec16, W16 = _operands_bf16(enc_, dec_, W_)
-        b32 = bias.detach().to(torch.float32).contiguous()
-        B, T, _ = enc16.shape
-        U = dec16.shape[1]
-        lat2, logz = ops.joint_fwd(enc16, dec16, W16, b32, targets, logit_lengths, target_lengths, blank, act_kind, act_param)
-        alpha, beta, cost, _, _ = ops.alpha_beta(lat2, logit_lengths, target_lengths, B, T, U)
-        ctx.save_for_backward(enc16, dec16, W16, b32, targets, logit_lengths, target_lengths, lat2, logz, alpha, beta, cost)
+    def forward(ctx, enc, dec, W, bias, targets, logit_lengths, target_lengths, relative_lengths, blank, act_kind, act_param,
+                max_chunk_cells, prune_log2_eps=None, clamp=-1.0, check_lengths=True):
+        dev = enc.device
+        B, T, H = enc.shape
+        U, V = dec.shape[1], W.shape[0]
+        lib = _lib.load()
+        ops_ = (enc.detach(), dec.detach(), W.detach())
+        if H % 64 == 0 and all(t.dtype == torch.float32 and t.is_contiguous() and t.data_ptr() % 16 == 0 for t in ops_):
+            code = _lib.F32        # the recipe's case: converted inside the preparation kernel
+        elif H % 64 == 0 and all(t.dtype == torch.bfloat16 and t.is_contiguous() and t.data_ptr() % 16 == 0 for t in ops_):
+            code = _lib.BF16       # projections that already emit bf16 (autocast): used as they are
+        else:
+            # fp16 / mixed dtypes / strided views / H not a multiple of 64: one torch pass.  The kernels contract over whole
+            # 64-wide k-blocks; zero columns add nothing (act(0) = 0 for every fused activation, padded W columns are zero)
+            pad = (0, (-H) % 64)
+            ops_ = tuple(torch.nn.functional.pad(t, pad).to(torch.bfloat16).contiguous() if pad[1] else t.to(torch.bfloat16).contiguous()
+                         for t in ops_)
+            code = _lib.BF16
+        Hp = ops_[0].shape[-1]
+        b32 = bias.detach()
+        if b32.dtype != torch.float32 or not b32.is_contiguous():
+            b32 = b32.to(torch.float32).contiguous()
+        tg = targets
+        if tg.dtype not in (torch.int32, torch.int64) or not tg.is_contiguous():
+            tg = tg.to(torch.int32).contiguous()
+        n_targets = tg.shape[1]
+        if relative_lengths:
+            ll_in = logit_lengths if logit_lengths.dtype == torch.float32 and logit_lengths.is_contiguous() else logit_lengths.to(torch.float32).contiguous()
+            tl_in = target_lengths if target_lengths.dtype == torch.float32 and target_lengths.is_contiguous() else target_lengths.to(torch.float32).contiguous()
+            len_args = (ll_in.data_ptr(), tl_in.data_ptr(), None, None)
+        else:
+            ll_in = logit_lengths if logit_lengths.dtype == torch.int32 and logit_lengths.is_contiguous() else logit_lengths.to(torch.int32).contiguous()
+            tl_in = target_lengths if target_lengths.dtype == torch.int32 and target_lengths.is_contiguous() else target_lengths.to(torch.int32).contiguous()
+            len_args = (None, None, ll_in.data_ptr(), tl_in.data_ptr())
+        off = _fwd_layout(B, T, U, Hp, V)
+        scratch = torch.empty((off[7],), dtype=torch.uint8, device=dev)
+        n = ops.lattice_elems(B, T, U)
+        out = torch.empty((5 * n + 3 * B,), dtype=torch.float32, device=dev)  # lat2 | logz | alpha | beta | cost, ll_a, ll_b
+        lat2, logz, alpha, beta, cost3 = out[: 2 * n].view(n, 2), out[2 * n: 3 * n], out[3 * n: 4 * n], out[4 * n: 5 * n], out[5 * n:]
+        ring = _StatsRing.get(dev) if check_lengths else None
+        slot, seq, slot_ptr = ring.next_slot() if ring is not None else (0, 0, None)
+        with ops._on_device(dev):
+            _lib.check(lib.tsasr_joint_loss_fwd(
+                ops_[0].data_ptr(), ops_[1].data_ptr(), ops_[2].data_ptr(), code, b32.data_ptr(), tg.data_ptr() if tg.numel() else None,
+                1 if tg.dtype == torch.int64 else 0, *len_args, B, T, U, Hp, V, int(blank), int(act_kind), float(act_param),
+                scratch.data_ptr(), scratch.numel(), slot_ptr, seq, lat2.data_ptr(), logz.data_ptr(), alpha.data_ptr(), beta.data_ptr(),
+                cost3.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        if code == _lib.F32:
+            enc16 = scratch[off[0]: off[0] + 2 * B * T * Hp].view(torch.bfloat16).view(B, T, Hp)
+            dec16 = scratch[off[1]: off[1] + 2 * B * U * Hp].view(torch.bfloat16).view(B, U, Hp)
+            W16 = scratch[off[2]: off[2] + 2 * V * Hp].view(torch.bfloat16).view(V, Hp)
+        else:
+            enc16, dec16, W16 = ops_
+        tg32 = scratch[off[3]: off[3] + 4 * B * n_targets].view(torch.int32).view(B, n_targets) if tg.dtype == torch.int64 else tg
+        ll = scratch[off[4]: off[4] + 4 * B].view(torch.int32)
+        tl = scratch[off[5]: off[5] + 4 * B].view(torch.int32)
+        cost = cost3[:B]
+        ctx.save_for_backward(enc16, dec16, W16, b32, tg32, ll, tl, lat2, logz, alpha, beta, cost)
         ctx.cfg = (blank, act_kind, act_param, max_chunk_cells, prune_log2_eps, clamp)
         ctx.in_dtypes = (enc.dtype, dec.dtype, W.dtype, bias.dtype)
         ctx.H = H
-        return cost
+        ctx.mark_non_differentiable(ll, tl)
+        if ring is not None:
+            # torchaudio's argument checks: same exception types and messages, raised after the (length-clamping) kernels
+            # have been queued; the statistics arrive through mapped pinned memory, no synchronisation of the stream
+            _raise_length_errors(ring.wait(slot, seq, dev), T, U, n_targets)
+        return cost, ll, tl
 
     @staticmethod
-    def backward(ctx, dcost):
+    def backward(ctx, dcost, _dll=None, _dtl=None):
         enc16, dec16, W16, b32, targets, ll, tl, lat2, logz, alpha, beta, cost = ctx.saved_tensors
         blank, act_kind, act_param, max_chunk_cells, prune_log2_eps, clamp = ctx.cfg
         dcost = dcost.to(torch.float32).contiguous()
@@ -266,7 +390,7 @@ class FusedJointRnnt(torch.autograd.Function):
         de, dd, dw, dbt = ctx.in_dtypes
         if d_enc.shape[-1] != ctx.H:  # drop the gradients of the zero padding
             d_enc, d_dec, dW = d_enc[..., :ctx.H].contiguous(), d_dec[..., :ctx.H].contiguous(), dW[:, :ctx.H].contiguous()
-        return (d_enc.to(de), d_dec.to(dd), dW.to(dw), db.to(dbt), None, None, None, None, None, None, None, None, None)
+        return (d_enc.to(de), d_dec.to(dd), dW.to(dw), db.to(dbt)) + (None,) * 11
 
 
 class _NumbaReduce(torch.autograd.Function):
@@ -322,15 +446,11 @@ def fused_joint_rnnt_loss(enc_out, dec_out, weight, bias, targets, logit_lengths
         blank += V
     if not 0 <= blank < V:
         raise RuntimeError("blank must be within [0, logits.shape[-1])")
-    targets = targets.to(torch.int32).contiguous()
-    with ops._on_device(enc_out.device):
-        logit_lengths, target_lengths, stats, ready = _prepare_lengths(logit_lengths, target_lengths, T, targets.shape[1],
-                                                                       relative_lengths)
-        costs = FusedJointRnnt.apply(enc_out, dec_out, weight, bias, targets, logit_lengths, target_lengths, int(blank),
-                                     _lib.ACT_CODES[activation], float(act_param), int(max_chunk_cells), prune_log2_eps, float(clamp))
-        if check_lengths:
-            # raises what torchaudio raises; the kernels above are already queued
-            _DeferredLengthCheck(stats, ready).finish(T, U, targets.shape[1])
+    if targets.device != enc_out.device:
+        targets = targets.to(enc_out.device)
+    costs, logit_lengths, _ = FusedJointRnnt.apply(enc_out, dec_out, weight, bias, targets, logit_lengths, target_lengths,
+                                                bool(relative_lengths), int(blank), _lib.ACT_CODES[activation], float(act_param),
+                                                int(max_chunk_cells), prune_log2_eps, float(clamp), bool(check_lengths))
     if numba_semantics:
         return _NumbaReduce.apply(costs, logit_lengths, reduction)
     return _reduce(costs, reduction)
