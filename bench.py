@@ -238,7 +238,7 @@ def run_reference(args, rank):
     }))
 
 
-def kernel_lines(kernel_ms, cfg, peak_burst, peak_sust, peak_hbm, active_tiles=None, live_tiles=None):
+def kernel_lines(kernel_ms, cfg, peak_burst, peak_sust, peak_hbm, active_tiles=None, live_tiles=None, work_cells=None):
     """Per-kernel device time of one step (CUDA events inside the library, 5 extra steps after the timed region)
     with the bound that applies: GEMM kernels against the measured bf16 peaks (burst: the regime of this short timed
     region; sustained beside it), the lattice DP and the fold kernels against the measured HBM copy bandwidth
@@ -246,7 +246,7 @@ def kernel_lines(kernel_ms, cfg, peak_burst, peak_sust, peak_hbm, active_tiles=N
     the three backward GEMM kernels are credited the FLOPs they EXECUTE (2 * 128 * active tiles * H * V), so their
     fraction stays a statement about the kernel, not about the pruning."""
     B, T, U, V, H = (cfg[k] for k in "BTUVH")
-    cells = B * T * U
+    cells = work_cells if work_cells else B * T * U
     gemm = 2.0 * cells * H * V
     gemm_bwd = 2.0 * 128 * active_tiles * H * V if active_tiles else gemm
     tiles = active_tiles if active_tiles else B * ((T + 15) // 16) * ((U + 7) // 8)
@@ -402,8 +402,11 @@ def main():
         cfg["B"] = args.global_batch // world
     ragged = args.ragged or strong  # the strong-scaling arm is the ragged global batch of SURVEY 8e: the slowest rank is reported
     B, T, U, V, H = (cfg[k] for k in "BTUVH")
-    cells = B * T * U
+    cells = B * T * U  # the metric counts the padded lattice (BASELINE.json: B*T*U, U = logits.shape[2])
     enc, dec, Wt, bias, targets, ll, tl = synth(cfg, dev, seed=rank, ragged=ragged)
+    # cells that carry work: sum_b T_b * (labels_b + 1); the roofline lines credit FLOPs for these only (== cells when
+    # every utterance has the full length, the headline case)
+    work_cells = int((ll.long() * (tl.long() + 1)).sum().item())
     enc16, dec16, W16 = enc.bfloat16().contiguous(), dec.bfloat16().contiguous(), Wt.bfloat16().contiguous()
     dcost = torch.full((B,), 1.0 / (B * world), dtype=torch.float32, device=dev)
     act = _lib.ACT_CODES[cfg["act"]]
@@ -620,7 +623,7 @@ def main():
 
     if rank == 0:
         peak_burst, peak_sust, peak_hbm, peak_src = measured_peaks()
-        flops = 2.0 * cells * H * V  # algorithmic FLOPs of the forward joint GEMM launch
+        flops = 2.0 * work_cells * H * V  # algorithmic FLOPs of the forward joint GEMM launch (cells inside the T_b x U_b rectangles)
         achieved = flops / (fwd_ms / 1e3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -636,7 +639,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(cfg, args.shape, world, strong), "B_per_gpu": B, "T": T, "U": U, "V": V, "H": H,
-                       "lengths": "ragged (T_b in [0.6T,T], labels in [0.4U,U-1])" if ragged else "full", "activation": cfg["act"],
+                       "lengths": "ragged (T_b in [0.6T,T], labels in [0.4U,U-1])" if ragged else "full", "cells_with_work": work_cells, "activation": cfg["act"],
                        "parallelism": f"utterance-sharded dp{world}",
                        "l2": "flushed between timed steps with a 256 MiB write (untimed); step timed with CUDA events"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
@@ -660,7 +663,7 @@ def main():
                                         "frac_sustained": dense_tf / peak_sust,
                                         "what": "6MHV / ms_per_step of the run with tile pruning off"}},
             "clocks": clocks,
-            "kernels": kernel_lines(kernel_ms, cfg, peak_burst, peak_sust, peak_hbm, active_tiles, live_tiles),
+            "kernels": kernel_lines(kernel_ms, cfg, peak_burst, peak_sust, peak_hbm, active_tiles, live_tiles, work_cells),
         }
         out["config"]["backward_tile_pruning"] = (
             {"log2_eps": prune_eps, "active_tiles": active_tiles, "live_tiles": live_tiles,

@@ -113,7 +113,7 @@ def test_no_kernel_writes_outside_its_buffers(shape, chunk):
                                             p["lla"], p["llb"], st))
     _lib.check(lib.tsasr_joint_bwd(enc.data_ptr(), dec.data_ptr(), W.data_ptr(), bias.data_ptr(), targets.data_ptr(), ll.data_ptr(),
                                    tl.data_ptr(), B, T, U, H, V, 0, 0, 0.01, p["lat2"], p["logz"], p["alpha"], p["beta"], p["cost"],
-                                   dcost.data_ptr(), p["ws"], ws_bytes, chunk, -30.0, p["d_enc"], p["d_dec"], p["dW"], p["db"], st))
+                                   dcost.data_ptr(), p["ws"], ws_bytes, chunk, -30.0, -1.0, p["d_enc"], p["d_dec"], p["dW"], p["db"], st))
     torch.cuda.synchronize()
     for k, (buf, view, start) in bufs.items():
         assert _guards_intact(buf, start, sizes[k]), f"canary band around {k} was overwritten"

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 GPU session 3: full GPU suite on the single-call forward + fused clamp + on-device greedy; host timeline; bench
 mkdir -p gpurun_out
-timeout 2400 python -m pytest tests -m gpu -q -rf --durations=6 -x > gpurun_out/s3_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s3_pytest.log
+timeout 2400 python -m pytest tests -m gpu -q -rf --durations=6 > gpurun_out/s3_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s3_pytest.log
 timeout 300 python tools/profile_e2e_host.py > gpurun_out/s3_host_profile.log 2>&1; echo "rc=$?" >> gpurun_out/s3_host_profile.log
 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/s3_bench.json 2> gpurun_out/s3_bench.err; echo "bench rc=$?" >> gpurun_out/s3_bench.err
 timeout 300 python bench.py --no-cpu-baseline --no-reference-gpu --shape recipe > gpurun_out/s3_bench_recipe.json 2> gpurun_out/s3_bench_recipe.err

@@ -165,17 +165,88 @@ def greedy_decode_on_device(tn_output, decode_network_lst, joint_step, blank_id=
     return hyps, score, None, None
 
 
+def greedy_decode_cuda_graph(tn_output, decode_network_lst, joint_step, blank_id=0):
+    """``greedy_decode_on_device`` with the per-frame body captured ONCE in a CUDA graph and replayed T times: a frame is
+    one graph launch instead of ~25 kernel launches (the body is launch-bound: tiny kernels over B rows).  The frame
+    index lives on the device and is advanced inside the graph, all state is updated in place in static buffers.
+    Same results as ``greedy_decode_on_device``; falls back to it when capture is not possible (e.g. a prediction
+    network whose kernels cannot be captured)."""
+    B, T = tn_output.shape[0], tn_output.shape[1]
+    dev = tn_output.device
+    if not tn_output.is_cuda or T < 8:
+        return greedy_decode_on_device(tn_output, decode_network_lst, joint_step, blank_id)
+    try:
+        with torch.no_grad():
+            tn_t = tn_output.transpose(0, 1).contiguous()                                  # [T, B, H]: one row block per frame
+            input_pn0 = torch.full((B, 1), int(blank_id), device=dev, dtype=torch.int32)
+            out_pn0, hidden0 = _forward_pn(input_pn0, decode_network_lst)
+            hidden0 = hidden0 if isinstance(hidden0, tuple) else (hidden0,)
+            state = {"t": torch.zeros((1,), device=dev, dtype=torch.int64), "input_pn": input_pn0.clone(), "out_pn": out_pn0.clone(),
+                     "hidden": tuple(h.clone() for h in hidden0), "scores": torch.zeros((B,), device=dev, dtype=torch.float32),
+                     "emitted": torch.full((T, B), int(blank_id), device=dev, dtype=torch.int64)}
+
+            def reset():
+                state["t"].zero_()
+                state["input_pn"].copy_(input_pn0)
+                state["out_pn"].copy_(out_pn0)
+                for h, h0 in zip(state["hidden"], hidden0):
+                    h.copy_(h0)
+                state["scores"].zero_()
+
+            def body():
+                frame = torch.index_select(tn_t, 0, state["t"]).squeeze(0)                 # [B, H]
+                log_probs = joint_step(frame.unsqueeze(1).unsqueeze(1), state["out_pn"].unsqueeze(1))
+                logp, pos = torch.max(log_probs.reshape(B, -1), dim=1)
+                emit = pos != blank_id
+                state["emitted"].index_copy_(0, state["t"], pos.unsqueeze(0))
+                state["scores"].add_(torch.where(emit, logp.to(torch.float32), torch.zeros_like(logp, dtype=torch.float32)))
+                state["input_pn"].copy_(torch.where(emit.view(B, 1), pos.to(torch.int32).view(B, 1), state["input_pn"]))
+                hid = state["hidden"] if len(state["hidden"]) > 1 else state["hidden"][0]
+                new_out, new_hidden = _forward_pn(state["input_pn"], decode_network_lst, hid)
+                new_hidden = new_hidden if isinstance(new_hidden, tuple) else (new_hidden,)
+                state["out_pn"].copy_(torch.where(emit.view(B, 1, 1), new_out, state["out_pn"]))
+                for h, nh in zip(state["hidden"], new_hidden):
+                    h.copy_(torch.where(emit.view(1, B, 1), nh, h))
+                state["t"].add_(1)
+
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                                                 # warm-up outside capture (cuDNN plans, allocator)
+                for _ in range(3):
+                    body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            reset()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+            reset()
+            for _ in range(T):
+                graph.replay()
+            table = state["emitted"].t().cpu()
+            score = state["scores"].exp().mean().cpu()
+    except Exception as ex:  # noqa: BLE001  (capture failed: same search without the graph)
+        from .transducer_joint import _warn_once
+
+        _warn_once(f"CUDA-graph capture of the greedy frame body failed ({type(ex).__name__}: {str(ex)[:120]}); using the plain on-device loop")
+        return greedy_decode_on_device(tn_output, decode_network_lst, joint_step, blank_id)
+    hyps = [[int(x) for x in row[row != blank_id].tolist()] for row in table]
+    return hyps, score, None, None
+
+
 def patch_searcher(searcher, on_device_greedy=False):
     """Replace ``searcher._joint_forward_step`` by the fused step (returns True when patched).
     ``on_device_greedy``: additionally replace the greedy searcher (``beam_size <= 1``) by ``greedy_decode_on_device``
-    -- same hypotheses and score, no per-frame host synchronisation."""
+    -- same hypotheses and score, no per-frame host synchronisation; ``"graph"`` selects the CUDA-graph variant (one
+    graph launch per frame)."""
     step = fused_joint_forward_step(searcher.tjoint, searcher.classifier_network, searcher.softmax)
     if step is None:
         return False
     searcher._joint_forward_step = types.MethodType(lambda self, h_i, out_PN: step(h_i, out_PN), searcher)
     if on_device_greedy and getattr(searcher, "beam_size", 2) <= 1:
+        search = greedy_decode_cuda_graph if on_device_greedy == "graph" else greedy_decode_on_device
+
         def greedy(self, tn_output):
-            return greedy_decode_on_device(tn_output, self.decode_network_lst, self._joint_forward_step, self.blank_id)
+            return search(tn_output, self.decode_network_lst, self._joint_forward_step, self.blank_id)
 
         searcher.transducer_greedy_decode = types.MethodType(greedy, searcher)
         searcher.searcher = searcher.transducer_greedy_decode
