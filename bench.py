@@ -402,8 +402,20 @@ def main():
         cfg["B"] = args.global_batch // world
     ragged = args.ragged or strong  # the strong-scaling arm is the ragged global batch of SURVEY 8e: the slowest rank is reported
     B, T, U, V, H = (cfg[k] for k in "BTUVH")
+    if strong:
+        # ONE global batch (fixed seed, ragged), dealt to the ranks in contiguous chunks of utterances;
+        # every rank pads to the longest utterance of ITS chunk, as the recipe's per-rank collate function does
+        gcfg = dict(cfg, B=args.global_batch)
+        g_enc, g_dec, Wt, bias, g_tg, g_ll, g_tl = synth(gcfg, "cpu", seed=0, ragged=True)
+        sl = slice(rank * B, (rank + 1) * B)
+        ll, tl = g_ll[sl].clone(), g_tl[sl].clone()
+        T, U = int(ll.max()), int(tl.max()) + 1
+        enc, dec, targets = g_enc[sl, :T].contiguous(), g_dec[sl, :U].contiguous(), g_tg[sl, : U - 1].contiguous()
+        enc, dec, Wt, bias, targets, ll, tl = (x.to(dev) for x in (enc, dec, Wt, bias, targets, ll, tl))
+        cfg.update(T=T, U=U)
+    else:
+        enc, dec, Wt, bias, targets, ll, tl = synth(cfg, dev, seed=rank, ragged=ragged)
     cells = B * T * U  # the metric counts the padded lattice (BASELINE.json: B*T*U, U = logits.shape[2])
-    enc, dec, Wt, bias, targets, ll, tl = synth(cfg, dev, seed=rank, ragged=ragged)
     # cells that carry work: sum_b T_b * (labels_b + 1); the roofline lines credit FLOPs for these only (== cells when
     # every utterance has the full length, the headline case)
     work_cells = int((ll.long() * (tl.long() + 1)).sum().item())
@@ -469,7 +481,12 @@ def main():
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     ms_per_step = max_over_ranks(sum(s.elapsed_time(e) for s, e in evs)) / K
-    value = world * cells / (ms_per_step / 1e3)
+    total_cells = world * cells  # whole-job lattice cells per step
+    if strong and dist is not None:  # every rank pads to its own longest utterance: add the per-rank lattices up
+        tc = torch.tensor([float(cells)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tc)
+        total_cells = int(tc.item())
+    value = total_cells / (ms_per_step / 1e3)
     fwd_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in fwd_ev)
 
     # ---- the same steps with backward tile pruning switched off (reported beside the headline, not instead of it) ----
@@ -514,7 +531,7 @@ def main():
             s_sampler.mark_end()
         s_ms = max_over_ranks(s.elapsed_time(e)) / n_target
         sustained = {"seconds": s_ms * n_target / 1e3, "steps": n_target, "ms_per_step": s_ms,
-                     "value": world * cells / (s_ms / 1e3), "unit": UNIT, "clocks": s_sampler.stop() if s_sampler else None,
+                     "value": total_cells / (s_ms / 1e3), "unit": UNIT, "clocks": s_sampler.stop() if s_sampler else None,
                      "what": "back-to-back steps for seconds, no L2 flush, CUDA events around the whole loop, max over ranks"}
         fence()
 
@@ -580,7 +597,7 @@ def main():
     e.record()
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks(s.elapsed_time(e) / Ke)
-    e2e_value = world * cells / (e2e_ms / 1e3)
+    e2e_value = total_cells / (e2e_ms / 1e3)
 
     # ---- N > 1: the head gradient DDP produced must be the rank average of the local gradients ----
     ddp_check = None
@@ -671,7 +688,7 @@ def main():
                      "backward (every dlogits term carries that factor; below fp32 resolution of the kept terms); "
                      "TSASR_PRUNE_LOG2_EPS=0 switches it off"} if prune_eps < 0 else "off")
         if dense_ms is not None:
-            out["dense_backward"] = {"ms_per_step": dense_ms, "value": world * cells / (dense_ms / 1e3), "unit": UNIT,
+            out["dense_backward"] = {"ms_per_step": dense_ms, "value": total_cells / (dense_ms / 1e3), "unit": UNIT,
                                      "what": "same steps with tile pruning off (every live tile recomputed and fed to the GEMMs)"}
         if sustained is not None:
             sust_tf = (flops + 2.0 * bwd_exec) / (sustained["ms_per_step"] / 1e3) / 1e12
