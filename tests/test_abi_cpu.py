@@ -139,3 +139,26 @@ def test_install_into_speechbrain_patches_the_three_import_names(monkeypatch):
     assert mods["speechbrain.nnet.transducer.transducer_joint"].Transducer_joint is tsasr_b200.Transducer_joint
     assert mods["speechbrain.nnet.loss.transducer_loss"].TransducerLoss is tsasr_b200.TransducerLoss
     assert mods["speechbrain.nnet.loss.transducer_loss"].Transducer is tsasr_b200.Transducer
+
+
+def test_deferred_finite_check_keeps_the_reference_bookkeeping():
+    """tsasr_b200.monitor: CPU tensors fall through to the original check; the deferred path (exercised with a stub
+    that pretends to be a CUDA loss is covered on the GPU by tests/test_insitu_gpu.py)."""
+    import torch
+
+    import tsasr_b200
+
+    class Brain:
+        def __init__(self):
+            self.calls = []
+
+        def check_gradients(self, loss):
+            self.calls.append(float(loss))
+            return bool(loss.isfinite())
+
+    b = Brain()
+    chk = tsasr_b200.monitor.install(b)
+    assert b.check_gradients(torch.tensor(1.0)) is True and b.check_gradients(torch.tensor(float("nan"))) is False
+    assert len(b.calls) == 2 and chk.deferred_steps == 0
+    tsasr_b200.monitor.uninstall(b)
+    assert b.check_gradients.__func__ is Brain.check_gradients

@@ -140,3 +140,23 @@ def test_on_device_greedy_with_fused_step_vs_reference_golden(golden):
     got_h, got_s, _, _ = searcher.searcher(tn2)
     assert got_h == ref_h
     np.testing.assert_allclose(float(got_s), np.exp(np.array(ref_s)).mean(), rtol=1e-4)
+
+
+@pytest.mark.gpu
+def test_cuda_graph_greedy_matches_the_plain_on_device_loop(golden):
+    """One CUDA-graph launch per frame (frame index advanced on the device inside the graph): same hypotheses and score
+    as the reference's searcher (golden vector) and as the plain on-device loop on a longer random problem."""
+    g = golden("greedy_decode")
+    d = torch.device("cuda:0")
+    pred, head, tjoint, tn, hyps = _golden_modules(g, d)
+    torch.backends.cudnn.allow_tf32 = False
+    step = decode.fused_joint_forward_step(tjoint, [head], torch.nn.LogSoftmax(dim=-1))
+    got, score, _, _ = decode.greedy_decode_cuda_graph(tn, pred.layers(), step, blank_id=0)
+    assert got == hyps
+    np.testing.assert_allclose(float(score), float(g["mean_exp_score"]), rtol=1e-4)
+    gen = torch.Generator().manual_seed(6)
+    tn2 = (1.5 * torch.randn(5, 90, tn.shape[2], generator=gen)).to(d)
+    want_h, want_s, _, _ = decode.greedy_decode_on_device(tn2, pred.layers(), step, blank_id=0)
+    got_h, got_s, _, _ = decode.greedy_decode_cuda_graph(tn2, pred.layers(), step, blank_id=0)
+    assert got_h == want_h
+    np.testing.assert_allclose(float(got_s), float(want_s), rtol=1e-5)

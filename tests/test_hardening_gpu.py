@@ -187,3 +187,28 @@ def test_fused_path_clamp_matches_the_compat_kernels(reduction):
     for got, ref, free in zip(outs[clamp], (e2.grad, dc2.grad, w2.grad, bb2.grad), outs[-1.0]):
         assert ((got - ref).abs().max() / ref.abs().max()).item() < 3e-3
         assert ((got - free).abs().max() / free.abs().max()).item() > 5e-2   # the clamp changed the gradients
+
+
+def test_deferred_finite_check_reports_one_step_late_without_syncing():
+    """tsasr_b200.monitor: the check of step i is resolved when step i+1's check runs; a non-finite loss
+    reaches the reference's own bookkeeping (here a stub of Brain.check_gradients, SB/core.py:1115-1150) one step later."""
+    d = _dev()
+
+    class Brain:
+        def __init__(self):
+            self.seen = []
+
+        def check_gradients(self, loss):
+            self.seen.append(float(loss))
+            return bool(loss.isfinite())
+
+    b = Brain()
+    chk = tsasr_b200.monitor.install(b)
+    assert b.check_gradients(torch.tensor(1.0, device=d)) is True            # nothing pending yet
+    assert b.check_gradients(torch.tensor(float("nan"), device=d)) is True   # resolves step 0 (finite); NaN is pending
+    assert b.seen == []                                                       # the original check has not run (no sync path)
+    assert b.check_gradients(torch.tensor(2.0, device=d)) is False           # resolves the NaN step through the original check
+    assert len(b.seen) == 1 and b.seen[0] != b.seen[0]
+    assert chk.flush() is True and chk.deferred_steps == 3
+    tsasr_b200.monitor.uninstall(b)
+    assert b.check_gradients(torch.tensor(3.0, device=d)) is True and b.seen[-1] == 3.0

@@ -154,7 +154,7 @@ def make_batch(sb, B, seconds, n_labels, V, seed, ragged=False):
     return PaddedBatch(items)
 
 
-def make_brain(sb, rec, ConformerEncoder, V, dropin, device, distributed, grad_accumulation_factor, seed, dropout):
+def make_brain(sb, rec, ConformerEncoder, V, dropin, device, distributed, grad_accumulation_factor, seed, dropout, deferred_check=False):
     torch.manual_seed(seed)  # identical initial weights in both arms (and on every rank, as DDP would broadcast them)
     mods = build_modules(sb, ConformerEncoder, V, dropin, dropout)
     hparams = build_hparams(sb, dropin, grad_accumulation_factor)
@@ -169,6 +169,10 @@ def make_brain(sb, rec, ConformerEncoder, V, dropin, device, distributed, grad_a
     brain.grad_norm_epoch, brain.nonfinite_count = [], 0   # what _fit_train sets up (SB/core.py:1181-1186)
     if not hasattr(brain, "valid_step"):
         brain.valid_step = 0
+    if deferred_check:  # N4: the loss.isfinite() host sync between forward and backward (SB/core.py:1072,1130) deferred by one step
+        import tsasr_b200
+
+        tsasr_b200.monitor.install(brain)
     return brain
 
 
@@ -202,9 +206,10 @@ def parity_cycle(brain, batches, grad_accumulation_factor, seed):
     return losses, captured
 
 
-def run_arm(sb, rec, ConformerEncoder, args, dropin, device, world):
+def run_arm(sb, rec, ConformerEncoder, args, dropin, device, world, deferred_check=False):
     """-> dict(ms_per_step, peak_mem_gib, losses, gradients of the first accumulation cycle)."""
-    brain = make_brain(sb, rec, ConformerEncoder, args.vocab, dropin, device, world > 1, args.grad_accumulation_factor, args.seed, args.dropout)
+    brain = make_brain(sb, rec, ConformerEncoder, args.vocab, dropin, device, world > 1, args.grad_accumulation_factor, args.seed, args.dropout,
+                       deferred_check)
     rank = int(os.environ.get("RANK", "0"))
     batches = [make_batch(sb, args.batch, args.seconds, args.labels, args.vocab, seed=1000 * rank + i, ragged=args.ragged)
                for i in range(4)]
@@ -260,6 +265,8 @@ def main():
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--ragged", action="store_true")
+    ap.add_argument("--deferred-check", dest="deferred_check", action="store_true",
+                    help="third arm: drop-ins + tsasr_b200.monitor.install(brain) (no loss.isfinite() host sync between forward and backward)")
     args = ap.parse_args()
     rank, world, local_rank = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local_rank)
@@ -276,6 +283,8 @@ def main():
         res["stock"] = run_arm(sb, rec, ConformerEncoder, args, False, device, world)
     if args.arm in ("both", "dropin"):
         res["dropin"] = run_arm(sb, rec, ConformerEncoder, args, True, device, world)
+        if args.deferred_check:
+            res["dropin_deferred_check"] = run_arm(sb, rec, ConformerEncoder, args, True, device, world, deferred_check=True)
     if rank == 0:
         cells = args.batch * world  # utterances per step over all ranks
         out = {"what": "full fit_batch of train_librispeechmix_scratch.py TSASR (causal Conformer, injection_mode=cat, V=%d), "
@@ -284,9 +293,13 @@ def main():
                "n_gpus": world, "utterances_per_step": cells}
         for k, v in res.items():
             out[k] = {kk: vv for kk, vv in v.items() if not isinstance(vv, torch.Tensor)}
-        if len(res) == 2:
+        if "stock" in res and "dropin" in res:
             out["parity"] = compare(res["stock"], res["dropin"])
             out["speedup_fit_batch"] = res["stock"]["ms_per_step"] / res["dropin"]["ms_per_step"]
+        if "dropin_deferred_check" in res:
+            out["parity_deferred_check_vs_dropin"] = compare(res["dropin"], res["dropin_deferred_check"])
+            if "stock" in res:
+                out["speedup_fit_batch_deferred_check"] = res["stock"]["ms_per_step"] / res["dropin_deferred_check"]["ms_per_step"]
         print(json.dumps(out))
     if world > 1:
         torch.distributed.barrier()

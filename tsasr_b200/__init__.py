@@ -10,7 +10,7 @@ plus the functional forms ``rnnt_loss`` (torchaudio signature) and ``fused_joint
 All arithmetic runs in libtsasr_b200.so (hand-written CUDA, C ABI in include/tsasr_b200.h); there
 is no CPU path and no PyTorch fallback for the loss.
 """
-from . import _lib, ops  # noqa: F401
+from . import _lib, monitor, ops  # noqa: F401
 from .functional import fused_joint_rnnt_loss, rnnt_loss  # noqa: F401
 from .losses import Transducer, TransducerLoss, transducer_loss  # noqa: F401
 from .transducer_joint import JointHandle, Transducer_joint  # noqa: F401
