@@ -442,3 +442,40 @@ def test_fused_path_fuzz_vs_compat_path():
         np.testing.assert_allclose(costs.detach().cpu().numpy(), costs2.detach().cpu().numpy(), rtol=LOSS_RTOL, err_msg=tag)
         for got, ref, name in ((e.grad, e2.grad, "d_enc"), (dc.grad, dc2.grad, "d_dec"), (w.grad, w2.grad, "dW"), (bb.grad, bb2.grad, "db")):
             assert _rel_err(got, ref) < GRAD_REL, (tag, name, _rel_err(got, ref))
+
+
+def test_concat_joint_with_linear_joint_network_is_fused_as_a_sum_of_projections():
+    """``Transducer_joint(joint="concat", joint_network=Linear)`` (SB/nnet/transducer/transducer_joint.py:76-93): the
+    drop-in applies the two halves of the Linear to the encoder / predictor rows and runs the fused "sum" path; the
+    reference expands, concatenates and runs the Linear over all B*T*U rows.  Same loss (1e-4) and gradients -- including
+    the joint network's own -- against that eager math on the same bf16-representable operands."""
+    d = _dev()
+    g = torch.Generator().manual_seed(12)
+    B, T, U, He, Hd, Hj, V = 3, 33, 9, 48, 80, 128, 60
+    enc = (0.5 * torch.randn(B, T, He, generator=g)).to(d)
+    dec = (0.5 * torch.randn(B, U, Hd, generator=g)).to(d)
+    targets = torch.randint(1, V, (B, U - 1), generator=g).to(d)
+    il = torch.tensor([1.0, 0.7, 0.9], device=d)
+    tl = torch.tensor([1.0, 0.5, 0.25], device=d)
+
+    def run(fused):
+        torch.manual_seed(3)
+        jn = torch.nn.Linear(He + Hd, Hj).to(d)
+        head = torch.nn.Linear(Hj, V).to(d)
+        joiner = tsasr_b200.Transducer_joint(joint_network=jn, joint="concat", nonlinearity=torch.nn.LeakyReLU)
+        e, dc = enc.clone().requires_grad_(), dec.clone().requires_grad_()
+        if fused:
+            logits = head(joiner(e[..., None, :], dc[:, None, ...]))
+            assert isinstance(logits, tsasr_b200.JointHandle) and logits.has_head
+        else:
+            logits = head(joiner._eager(e[..., None, :], dc[:, None, ...]))            # the reference's expand + cat + Linear
+            assert logits.shape == (B, T, U, V)
+        loss = tsasr_b200.transducer_loss(logits, targets, il, tl, blank_index=0, reduction="mean", use_torchaudio=True)
+        loss.backward()
+        return loss.item(), [x.grad.clone() for x in (e, dc, jn.weight, jn.bias, head.weight, head.bias)]
+
+    loss_f, grads_f = run(True)
+    loss_e, grads_e = run(False)
+    assert abs(loss_f - loss_e) < 3e-4 * abs(loss_e)   # the eager arm keeps fp32 operands, the fused arm rounds them to bf16
+    for a, b_ in zip(grads_f, grads_e):
+        assert _rel_err(a, b_) < 1e-2

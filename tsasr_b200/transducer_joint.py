@@ -148,8 +148,27 @@ class Transducer_joint(nn.Module):
     def init_params(self, first_input):
         self.joint_network(first_input)
 
-    def _deferrable(self, input_TN, input_PN):
-        if self.joint != "sum" or input_TN.dim() != 4 or not (input_TN.is_cuda and input_PN.is_cuda):
+    def _concat_as_sum(self, input_TN, input_PN):
+        """``joint="concat"`` with a single Linear ``joint_network`` (transducer_joint.py:76-93) IS a "sum" joint of two
+        projections: ``W_j [e; d] + b = (W_j[:, :He] e + b) + W_j[:, He:] d``.  The reference expands both tensors to
+        [B,T,U,He+Hd], concatenates and runs the Linear over all B*T*U rows; here the two halves of ``W_j`` are applied to
+        the B*T encoder rows and the B*U predictor rows (plain ``F.linear``: autograd carries the gradient back into
+        ``joint_network``), and the rest is the fused "sum" path.  Returns the projected pair or None."""
+        if self.joint != "concat" or self.joint_network is None or input_TN.dim() != 4:
+            return None
+        lin = getattr(self.joint_network, "w", self.joint_network)  # SpeechBrain's Linear keeps its nn.Linear in .w
+        if type(lin) is not nn.Linear or not (input_TN.is_cuda and input_PN.is_cuda):
+            return None
+        if getattr(self.joint_network, "combine_dims", False):
+            return None
+        He, Hd = input_TN.shape[-1], input_PN.shape[-1]
+        if lin.in_features != He + Hd or input_TN.shape[2] != 1 or input_PN.shape[1] != 1:
+            return None
+        W = lin.weight
+        return torch.nn.functional.linear(input_TN, W[:, :He], lin.bias), torch.nn.functional.linear(input_PN, W[:, He:])
+
+    def _deferrable(self, input_TN, input_PN, as_sum=False):
+        if (self.joint != "sum" and not as_sum) or input_TN.dim() != 4 or not (input_TN.is_cuda and input_PN.is_cuda):
             return None
         if input_TN.shape[2] != 1 or input_PN.shape[1] != 1 or input_TN.shape[0] != input_PN.shape[0]:
             return None
@@ -178,12 +197,18 @@ class Transducer_joint(nn.Module):
         if act is not None:
             _lib.load()  # fail loudly here if the CUDA extension is missing
             return JointHandle(input_TN, input_PN, self.nonlinearity, act[0], act[1])
+        pair = self._concat_as_sum(input_TN, input_PN)
+        if pair is not None:
+            act = self._deferrable(*pair, as_sum=True)  # the deferral rules of the "sum" path apply to the projected pair
+            if act is not None:
+                _lib.load()
+                return JointHandle(pair[0], pair[1], self.nonlinearity, act[0], act[1])
 
         return self._eager(input_TN, input_PN)
 
     def _eager(self, tn, pn):
-        """The reference's eager math for every non-deferred case (decode-time shapes, CPU tensors,
-        ``concat`` joints, activations the fused prologue does not implement)."""
+        """The reference's eager math for every non-deferred case (decode-time shapes, CPU tensors, ``concat`` joints
+        without a single-Linear ``joint_network``, activations the fused prologue does not implement)."""
         if self.joint == "sum":
             joint = tn + pn  # broadcast add, transducer_joint.py:73-74
         elif self.joint == "concat":
