@@ -124,7 +124,7 @@ def test_no_kernel_writes_outside_its_buffers(shape, chunk):
 
 def test_unsupported_shapes_fail_where_the_call_is_made():
     d = _dev()
-    U = 1030  # > 1024 lattice columns
+    U = 8200  # wider than the DP's shared-memory diagonal buffers allow (kMaxLatticeWidth = 8192)
     enc = torch.zeros(1, 4, 64, device=d)
     dec = torch.zeros(1, U, 64, device=d)
     W = torch.zeros(8, 64, device=d)
@@ -139,6 +139,46 @@ def test_unsupported_shapes_fail_where_the_call_is_made():
     h = joiner(torch.zeros(1, 3, 1, 64, device=d), torch.zeros(1, 1, 2, 64, device=d))
     out = torch.nn.functional.linear(h, torch.zeros(1, 64, device=d))
     assert not isinstance(out, tsasr_b200.JointHandle) and out.shape == (1, 3, 2, 1)
+
+
+@pytest.mark.parametrize("T,U", [(7, 1500), (40, 1025), (3, 3000)])
+def test_wide_lattices_beyond_1024_columns_vs_torchaudio(T, U):
+    """U > 1024 (more label positions than one thread block has threads): the DP switches to alpha_beta_wide_kernel
+    (several columns per thread).  torchaudio's path has no such limit (the reference's Numba path does); loss and dlogits
+    against torchaudio's CPU rnnt_loss, compat and fused paths."""
+    from torchaudio.functional import rnnt_loss as ta_rnnt_loss
+
+    g = torch.Generator().manual_seed(T * U)
+    B, V = 2, 6
+    logits = torch.randn(B, T, U, V, generator=g)
+    targets = torch.randint(1, V, (B, U - 1), generator=g, dtype=torch.int32)
+    ll = torch.tensor([T, max(1, T - 2)], dtype=torch.int32)
+    tl = torch.tensor([U - 1, U - 300], dtype=torch.int32)
+    ref_x = logits.clone().requires_grad_()
+    ref = ta_rnnt_loss(ref_x, targets, ll, tl, blank=0, reduction="none")
+    ref.sum().backward()
+    d = _dev()
+    x = logits.to(d).requires_grad_()
+    got = tsasr_b200.rnnt_loss(x, targets.to(d), ll.to(d), tl.to(d), blank=0, reduction="none")
+    got.sum().backward()
+    np.testing.assert_allclose(got.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-4)
+    assert (x.grad.cpu() - ref_x.grad).abs().max().item() < 1e-3
+    # the two DP directions agree on log P through the C ABI
+    lat2, den = ops.logits_to_lattice(logits.to(d), targets.to(d), ll.to(d), tl.to(d), 0)
+    _, _, cost, ll_a, ll_b = ops.alpha_beta(lat2, ll.to(d), tl.to(d), B, T, U)
+    np.testing.assert_allclose(ll_a.cpu().numpy(), ll_b.cpu().numpy(), rtol=1e-5)
+    # fused path at the same width (H = 64, tiny head)
+    gen = torch.Generator().manual_seed(1)
+    enc = (0.5 * torch.randn(B, T, 64, generator=gen)).bfloat16()
+    dec = (0.5 * torch.randn(B, U, 64, generator=gen)).bfloat16()
+    W = ((torch.rand(V, 64, generator=gen) * 2 - 1) / 8).bfloat16()
+    bias = torch.zeros(V)
+    from oracle.reference_chain import reference_joint_loss_fwd_bwd
+
+    costs = tsasr_b200.fused_joint_rnnt_loss(enc.to(d).float(), dec.to(d).float(), W.to(d).float(), bias.to(d), targets.to(d), ll.to(d), tl.to(d),
+                                             blank=0, reduction="none")
+    want = reference_joint_loss_fwd_bwd(enc, dec, W, bias, targets, ll, tl, 0, "leaky_relu", 0.01, round_bf16=True)
+    np.testing.assert_allclose(costs.cpu().numpy(), want["costs"].numpy(), rtol=1e-4)
 
 
 def test_two_devices_in_one_process_use_their_own_launch_attributes():

@@ -447,8 +447,12 @@ def test_fused_path_fuzz_vs_compat_path():
 def test_concat_joint_with_linear_joint_network_is_fused_as_a_sum_of_projections():
     """``Transducer_joint(joint="concat", joint_network=Linear)`` (SB/nnet/transducer/transducer_joint.py:76-93): the
     drop-in applies the two halves of the Linear to the encoder / predictor rows and runs the fused "sum" path; the
-    reference expands, concatenates and runs the Linear over all B*T*U rows.  Same loss (1e-4) and gradients -- including
-    the joint network's own -- against that eager math on the same bf16-representable operands."""
+    reference expands, concatenates and runs the Linear over all B*T*U rows.
+    (1) The rewrite is exact: bit-identical to the fused "sum" joint fed with the two projections computed by hand.
+    (2) Against the reference's eager math (fp32 throughout): loss within 3e-4; gradients in relative L2 -- the projected
+        operands are not bf16-representable here, so wherever the rounding flips the sign of a pre-activation LeakyReLU's
+        derivative jumps between 1 and 0.01 for that ELEMENT (the price of the bf16 joint BASELINE.json specifies), which
+        a max-norm over a 9-term sum shows at the percent level while the L2 norm stays small."""
     d = _dev()
     g = torch.Generator().manual_seed(12)
     B, T, U, He, Hd, Hj, V = 3, 33, 9, 48, 80, 128, 60
@@ -458,24 +462,32 @@ def test_concat_joint_with_linear_joint_network_is_fused_as_a_sum_of_projections
     il = torch.tensor([1.0, 0.7, 0.9], device=d)
     tl = torch.tensor([1.0, 0.5, 0.25], device=d)
 
-    def run(fused):
+    def run(mode):
         torch.manual_seed(3)
         jn = torch.nn.Linear(He + Hd, Hj).to(d)
         head = torch.nn.Linear(Hj, V).to(d)
         joiner = tsasr_b200.Transducer_joint(joint_network=jn, joint="concat", nonlinearity=torch.nn.LeakyReLU)
         e, dc = enc.clone().requires_grad_(), dec.clone().requires_grad_()
-        if fused:
+        if mode == "fused":
             logits = head(joiner(e[..., None, :], dc[:, None, ...]))
             assert isinstance(logits, tsasr_b200.JointHandle) and logits.has_head
-        else:
-            logits = head(joiner._eager(e[..., None, :], dc[:, None, ...]))            # the reference's expand + cat + Linear
+        elif mode == "by hand":  # the same two projections, then the fused "sum" joint
+            summer = tsasr_b200.Transducer_joint(joint="sum", nonlinearity=torch.nn.LeakyReLU)
+            ep = torch.nn.functional.linear(e[..., None, :], jn.weight[:, :He], jn.bias)
+            dp = torch.nn.functional.linear(dc[:, None, ...], jn.weight[:, He:])
+            logits = head(summer(ep, dp))
+            assert isinstance(logits, tsasr_b200.JointHandle) and logits.has_head
+        else:                    # the reference's expand + cat + Linear over all B*T*U rows
+            logits = head(joiner._eager(e[..., None, :], dc[:, None, ...]))
             assert logits.shape == (B, T, U, V)
         loss = tsasr_b200.transducer_loss(logits, targets, il, tl, blank_index=0, reduction="mean", use_torchaudio=True)
         loss.backward()
         return loss.item(), [x.grad.clone() for x in (e, dc, jn.weight, jn.bias, head.weight, head.bias)]
 
-    loss_f, grads_f = run(True)
-    loss_e, grads_e = run(False)
-    assert abs(loss_f - loss_e) < 3e-4 * abs(loss_e)   # the eager arm keeps fp32 operands, the fused arm rounds them to bf16
+    loss_f, grads_f = run("fused")
+    loss_h, grads_h = run("by hand")
+    loss_e, grads_e = run("eager")
+    assert loss_f == loss_h and all(torch.equal(a, b_) for a, b_ in zip(grads_f, grads_h))
+    assert abs(loss_f - loss_e) < 3e-4 * abs(loss_e)
     for a, b_ in zip(grads_f, grads_e):
-        assert _rel_err(a, b_) < 1e-2
+        assert ((a - b_).norm() / b_.norm()).item() < 5e-2

@@ -99,6 +99,10 @@ struct NvtxRange {
         if (!(cond)) return fail(TSASR_E_INVALID, __VA_ARGS__); \
     } while (0)
 
+// widest lattice the DP implements: up to 1024 columns one thread per column (alpha_beta_kernel), beyond that several
+// columns per thread with the diagonal double-buffered in shared memory (alpha_beta_wide_kernel: 2 * U floats)
+static constexpr int kMaxLatticeWidth = 8192;
+
 static int check_dims(int B, int T, int U, int V, int blank) {
     REQUIRE(B >= 1 && T >= 1 && U >= 1 && V >= 1, "B, T, U, V must be >= 1 (got %d %d %d %d)", B, T, U, V);
     REQUIRE(blank >= 0 && blank < V, "blank must be within [0, V) (got %d, V=%d)", blank, V);
@@ -375,7 +379,7 @@ int tsasr_lattice_alpha_beta(const float* lat2, const int32_t* logit_lengths, co
     NvtxRange nvtx_range("tsasr_lattice_alpha_beta");
     if (int rc = check_dims(B, T, U, 1, 0)) return rc;
     REQUIRE(lat2 && logit_lengths && target_lengths && alpha && beta && cost && ll_alpha && ll_beta, "null pointer argument");
-    if (U > 1024) return fail(TSASR_E_UNSUPPORTED, "lattice width U=%d > 1024 is not supported (the reference's Numba kernels share this limit)", U);
+    if (U > kMaxLatticeWidth) return fail(TSASR_E_UNSUPPORTED, "lattice width U=%d > %d is not supported", U, kMaxLatticeWidth);
     ScopedTiming tm("alpha_beta_kernel", static_cast<cudaStream_t>(stream));
     cudaError_t e = launch_alpha_beta(reinterpret_cast<const float2*>(lat2), logit_lengths, target_lengths, B, T, U,
                                       alpha, beta, ll_alpha, ll_beta, cost, static_cast<cudaStream_t>(stream));
@@ -467,7 +471,7 @@ int tsasr_joint_loss_fwd(const void* enc, const void* dec, const void* W, int op
     REQUIRE(operand_dtype == TSASR_F32 || operand_dtype == TSASR_BF16, "operands must be fp32 (converted here) or bf16 (used as they are)");
     REQUIRE((rel_logit_lengths || abs_logit_lengths) && (rel_target_lengths || abs_target_lengths), "null length argument");
     REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "scratch must be 256-byte aligned");
-    if (U > 1024) return fail(TSASR_E_UNSUPPORTED, "lattice width U=%d > 1024 is not supported", U);
+    if (U > kMaxLatticeWidth) return fail(TSASR_E_UNSUPPORTED, "lattice width U=%d > %d is not supported", U, kMaxLatticeWidth);
     size_t off[8];
     fwd_scratch_layout(B, T, U, H, V, off);
     if (scratch_bytes < off[7]) return fail(TSASR_E_WORKSPACE, "scratch too small: need %zu bytes, got %zu", off[7], scratch_bytes);

@@ -311,6 +311,66 @@ alpha_beta_kernel(const float2* __restrict__ lat2, const int* __restrict__ logit
     else dp_pass<true>(lat2 + base, beta + base, Tb, Ub, U, ll_beta + b, xchg, dp_ring);
 }
 
+// Wide lattices (U > 1024 columns: more than one thread block of columns).  Same recursion, simplest possible schedule:
+// one CTA per (utterance, direction), the previous anti-diagonal kept in shared memory (double buffered), every thread
+// takes the columns j, j + blockDim, ... of the current diagonal, one __syncthreads per diagonal.  Not tuned -- an
+// utterance with more than 1023 labels is far outside the recipe's range -- but it lifts the limit the reference's
+// torchaudio path does not have (its Numba path does: one thread per column as well).
+template <bool BETA>
+__device__ __forceinline__ void dp_pass_wide(const float2* __restrict__ lat, float* __restrict__ out, int Tb, int Ub, int U,
+                                             float* __restrict__ result, float* diag /* [2][U] */) {
+    const int S = Tb + Ub - 1;  // diagonals of the utterance's own rectangle
+    float* prev = diag;
+    float* cur = diag + U;
+    for (int s = 0; s < S; ++s) {
+        // alpha walks d = s upwards from cell (0,0); beta walks the mirrored lattice (t' = Tb-1-t, u' = Ub-1-u) the same way
+        for (int uu = threadIdx.x; uu < Ub; uu += blockDim.x) {
+            const int tt = s - uu;
+            if (tt < 0 || tt >= Tb) continue;
+            const int t = BETA ? Tb - 1 - tt : tt, u = BETA ? Ub - 1 - uu : uu;
+            const size_t o = (size_t)(t + u) * U + u;
+            float val;
+            if (BETA) {
+                const float2 cell = lat[o];
+                if (s == 0) {
+                    val = cell.x;  // beta(T-1, U-1) = lp_blank
+                } else {
+                    const float a = tt > 0 ? prev[uu] + cell.x : -INFINITY;        // beta(t+1, u) + lp_blank(t, u)
+                    const float b = uu > 0 ? prev[uu - 1] + cell.y : -INFINITY;    // beta(t, u+1) + lp_emit(t, u)
+                    val = logaddexp_fast(a, b);
+                }
+            } else {
+                if (s == 0) {
+                    val = 0.f;     // alpha(0, 0) = 0
+                } else {
+                    const float a = tt > 0 ? prev[uu] + lat[(size_t)(t - 1 + u) * U + u].x : -INFINITY;          // via blank from (t-1, u)
+                    const float b = uu > 0 ? prev[uu - 1] + lat[(size_t)(t + u - 1) * U + (u - 1)].y : -INFINITY;  // via emit from (t, u-1)
+                    val = logaddexp_fast(a, b);
+                }
+            }
+            cur[uu] = val;
+            out[o] = val;
+            if (s == S - 1) *result = BETA ? val : val + lat[o].x;  // log P: beta(0,0), or alpha(T-1,U-1) + lp_blank(T-1,U-1)
+        }
+        __syncthreads();
+        float* tmp = prev; prev = cur; cur = tmp;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+alpha_beta_wide_kernel(const float2* __restrict__ lat2, const int* __restrict__ logit_lengths,
+                       const int* __restrict__ target_lengths, int Tmax, int U, float* __restrict__ alpha,
+                       float* __restrict__ beta, float* __restrict__ ll_alpha, float* __restrict__ ll_beta) {
+    extern __shared__ __align__(16) float dp_diag[];  // [2][U]
+    griddep_wait();
+    const int b = blockIdx.x;
+    int Tb, Ub;
+    clamped_lengths(logit_lengths, target_lengths, b, Tmax, U, Tb, Ub);
+    const size_t base = (size_t)b * (size_t)(Tmax + U - 1) * (size_t)U;
+    if (blockIdx.y == 0) dp_pass_wide<false>(lat2 + base, alpha + base, Tb, Ub, U, ll_alpha + b, dp_diag);
+    else dp_pass_wide<true>(lat2 + base, beta + base, Tb, Ub, U, ll_beta + b, dp_diag);
+}
+
 // cost[b] = -log P from the beta pass (torchaudio: costs = -beta(0,0)); written by a tiny kernel so the
 // DP kernel keeps both log-likelihoods available for the consistency check in tests.
 __global__ void finalize_cost_kernel(const float* __restrict__ ll_beta, float* __restrict__ cost, int B) {
@@ -491,6 +551,15 @@ cudaError_t launch_logits_to_lattice(const void* logits, int dtype, const int* t
 
 cudaError_t launch_alpha_beta(const float2* lat2, const int* ll, const int* tl, int B, int Tmax, int U, float* alpha,
                               float* beta, float* ll_alpha, float* ll_beta, float* cost, cudaStream_t st) {
+    if (U > 1024) {  // wide lattice: several columns per thread (kMaxWideU bounds the shared-memory diagonal buffers)
+        const size_t diag_bytes = 2 * (size_t)U * sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(alpha_beta_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_bytes);
+        if (e != cudaSuccess) return e;
+        e = launch_pdl(alpha_beta_wide_kernel, dim3(B, 2), dim3(1024), diag_bytes, st, lat2, ll, tl, Tmax, U, alpha, beta, ll_alpha, ll_beta);
+        if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return e;
+        e = launch_pdl(finalize_cost_kernel, dim3((B + 127) / 128), dim3(128), 0, st, (const float*)ll_beta, cost, B);
+        return e != cudaSuccess ? e : cudaGetLastError();
+    }
     const int threads = ((U + 31) / 32) * 32;
     const size_t ring_bytes = (size_t)kDpPrefetch * threads * sizeof(float2);
     // per launch, like the GEMM launchers: the attribute is per DEVICE, and one process may drive several GPUs

@@ -17,15 +17,15 @@ def _check_reduction(reduction):
         raise ValueError('reduction should be one of "none", "mean", or "sum"')
 
 
-MAX_LATTICE_WIDTH = 1024  # alpha_beta_kernel: one thread per lattice column (the reference's Numba kernels share this limit)
+MAX_LATTICE_WIDTH = 8192  # kMaxLatticeWidth (csrc/capi.cu): one DP thread per column up to 1024, several columns per thread beyond
 
 
 def _check_lattice_shape(U, V):
     """Limits of the sm_100a kernels, rejected where the call is made -- not three launches later inside the C library."""
     if U > MAX_LATTICE_WIDTH:
         raise NotImplementedError(
-            f"tsasr_b200: lattice width U = max target length + 1 = {U} exceeds {MAX_LATTICE_WIDTH} (one DP thread per "
-            "lattice column); split the utterance or shorten the targets")
+            f"tsasr_b200: lattice width U = max target length + 1 = {U} exceeds {MAX_LATTICE_WIDTH} (the DP keeps two "
+            "anti-diagonals in shared memory); split the utterance or shorten the targets")
     if V < 2:
         raise ValueError(f"tsasr_b200: the vocabulary must hold the blank and at least one label (got V = {V})")
 
