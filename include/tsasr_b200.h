@@ -67,7 +67,10 @@ int tsasr_logits_to_lattice(const void* logits, int logits_dtype, const int32_t*
 /* Anti-diagonal wavefront forward/backward DP.  Replaces cu_kernel_forward / cu_kernel_backward
  * (SB/nnet/loss/transducer_loss.py:31-106,109-180) and torchaudio's ComputeAlphasBetasCosts.
  * Outputs alpha, beta (lattice-sized), cost[b] = -log P(y_b|x_b) (from beta(0,0)), and the two
- * log-likelihoods ll_alpha[b], ll_beta[b] (each B floats) for consistency checks. */
+ * log-likelihoods ll_alpha[b], ll_beta[b] (each B floats) for consistency checks.
+ * U <= 1024: one thread per lattice column, cp.async prefetch ring (the tuned kernel); 1024 < U <= 8192: several
+ * columns per thread, anti-diagonals double-buffered in shared memory (the reference's Numba kernels stop at 1024
+ * threads = columns, torchaudio has no limit); wider lattices return TSASR_E_UNSUPPORTED. */
 int tsasr_lattice_alpha_beta(const float* lat2, const int32_t* logit_lengths, const int32_t* target_lengths, int B,
                              int T, int U, float* alpha, float* beta, float* cost, float* ll_alpha, float* ll_beta,
                              tsasr_stream_t stream);
