@@ -163,10 +163,18 @@ def test_length_precondition_errors():
         tsasr_b200.rnnt_loss(logits.to(d), targets.to(d), (ll - 1).to(d), tl.to(d), blank=0)
     with pytest.raises(RuntimeError, match="output length mismatch"):
         tsasr_b200.rnnt_loss(logits.to(d), targets.to(d), ll.to(d), (tl - 1).to(d), blank=0)
-    with pytest.raises(NotImplementedError):
-        big = torch.zeros(1, 2, 1030, 4, device=d)
-        tsasr_b200.rnnt_loss(big, torch.ones(1, 1029, dtype=torch.int32, device=d), torch.tensor([2], dtype=torch.int32, device=d),
-                             torch.tensor([1029], dtype=torch.int32, device=d), blank=0)
+    # 1030 columns: beyond the one-thread-per-column DP (and the reference's Numba kernels), served by the wide DP kernel;
+    # uniform logits have the closed form -log P = (T + L) log V - log C(T - 1 + L, L)
+    import math
+
+    big = torch.zeros(1, 2, 1030, 4, device=d)
+    cost = tsasr_b200.rnnt_loss(big, torch.ones(1, 1029, dtype=torch.int32, device=d), torch.tensor([2], dtype=torch.int32, device=d),
+                                torch.tensor([1029], dtype=torch.int32, device=d), blank=0)
+    assert abs(cost.item() - ((2 + 1029) * math.log(4) - math.log(math.comb(1 + 1029, 1029)))) < 1e-4 * cost.item()
+    with pytest.raises(NotImplementedError):  # wider than the DP's shared-memory diagonals (8192 columns)
+        huge = torch.zeros(1, 1, 8200, 2, device=d)
+        tsasr_b200.rnnt_loss(huge, torch.ones(1, 8199, dtype=torch.int32, device=d), torch.tensor([1], dtype=torch.int32, device=d),
+                             torch.tensor([8199], dtype=torch.int32, device=d), blank=0)
 
 
 def test_full_size_properties_config2_lattice():
