@@ -15,7 +15,8 @@
 //   warp 18      pair partner only: relays "A block written" from its producer warps to the leader
 //   warps 8-15   A producers: build the 128-cell x H operand in shared memory in the canonical
 //                K-major SWIZZLE_128B layout (broadcast add + activation + bf16 round fused here) from enc/dec
-//                rows read straight from global memory (L1/L2 resident), one k-block prefetched ahead;
+//                rows read straight from global memory (L1/L2 resident): one enc load + four dec loads per thread and
+//                k-block (a thread's four rows share their frame), two k-blocks prefetched ahead;
 //                the operand stays resident for all N tiles of the cell tile
 //   warps 0-7    epilogue, two groups of four warps; both groups work on every accumulator buffer (2 x 256 TMEM
 //                columns), group g on columns [128 g, 128 g + 128).  MODE_FWD: online
@@ -193,7 +194,7 @@ __device__ __forceinline__ float act_t(float x, float param) {
 }
 
 // A producers: J k-blocks straight from enc / dec in global memory (L1/L2 resident: every enc row of a tile is
-// read by tU threads, every dec row by tT).  The loads of k-block kb+1 are issued before block kb is processed,
+// read by tU threads, every dec row by tT).  The loads run two k-blocks ahead of the block being processed,
 // so their latency hides behind the arithmetic and the a_empty wait.
 template <int MODE, int ACT, bool PAIR>
 __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a, const __nv_bfloat16* __restrict__ enc,
@@ -230,27 +231,41 @@ __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a,
             ++it;
             continue;
         }
+        // The four rows of a thread (rg, rg + 32, rg + 64, rg + 96) share their frame index ti (32 is a multiple of every
+        // tT), so they read the SAME enc row: one enc load + four dec loads per k-block instead of eight loads.  The
+        // registers that saves pay for a second k-block of prefetch (two register sets used alternately: set A holds the even
+        // k-blocks, set B the odd ones; a set is refilled with k-block kb + 2 right after k-block kb has been consumed),
+        // which matters where the producers pace the kernel (few vocabulary tiles per cell tile: V = 29 of the recipe as
+        // shipped) and trims their LSU instructions by 3/8 everywhere.
         bool ok[4];
-        const uint4* ep[4];
         const uint4* dp[4];
+        const int t_row = min(tc.t0 + ti[0], p.T - 1);
+        const uint4* ep = reinterpret_cast<const uint4*>(enc + ((size_t)tc.b * p.T + t_row) * p.H) + c;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             ok[i] = tc.t0 + ti[i] < tc.Tb && tc.u0 + ui[i] < tc.Ub;
             // rows outside the utterance are masked below; clamp them so that the loads stay inside the tensors
-            const int t = min(tc.t0 + ti[i], p.T - 1), u = min(tc.u0 + ui[i], p.U - 1);
-            ep[i] = reinterpret_cast<const uint4*>(enc + ((size_t)tc.b * p.T + t) * p.H) + c;
+            const int u = min(tc.u0 + ui[i], p.U - 1);
             dp[i] = reinterpret_cast<const uint4*>(dec + ((size_t)tc.b * p.U + u) * p.H) + c;
         }
-        uint4 ev[4], dv[4];
+        uint4 evA, dvA[4], evB = make_uint4(0, 0, 0, 0), dvB[4];
+        evA = __ldg(ep);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { ev[i] = __ldg(ep[i]); dv[i] = __ldg(dp[i]); }
-        for (int kb = 0; kb < KB; ++kb) {
-            uint4 o[4];
+        for (int i = 0; i < 4; ++i) { dvA[i] = __ldg(dp[i]); dvB[i] = make_uint4(0, 0, 0, 0); }
+        if (KB > 1) {  // next k-block: 64 h further = 8 chunks of 16 bytes
+            evB = __ldg(ep + 8);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t* e = reinterpret_cast<const uint32_t*>(&ev[i]);
+            for (int i = 0; i < 4; ++i) dvB[i] = __ldg(dp[i] + 8);
+        }
+        auto produce_block = [&](const int kb, uint4& ev, uint4 (&dv)[4]) {
+            mbar_wait(&a_empty[kb], (it & 1) ^ 1, 0x500 | kb);
+            uint8_t* blk = smem_a + kb * kABlockBytes;
+            const uint32_t* e = reinterpret_cast<const uint32_t*>(&ev);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {  // one row at a time: four live output registers instead of sixteen
                 const uint32_t* d = reinterpret_cast<const uint32_t*>(&dv[i]);
-                uint32_t* op = reinterpret_cast<uint32_t*>(&o[i]);
+                uint4 o;
+                uint32_t* op = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
                 for (int w = 0; w < 4; ++w) {
                     const float2 x = fadd2(make_float2(bf16_lo(e[w]), bf16_hi(e[w])), make_float2(bf16_lo(d[w]), bf16_hi(d[w])));
@@ -263,25 +278,26 @@ __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a,
                     }
                     op[w] = ok[i] ? pack_bf16x2(a.x, a.y) : 0u;
                 }
-            }
-            if (kb + 1 < KB) {  // next k-block: 64 h further = 8 chunks of 16 bytes
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { ev[i] = __ldg(ep[i] + (kb + 1) * 8); dv[i] = __ldg(dp[i] + (kb + 1) * 8); }
-            }
-            mbar_wait(&a_empty[kb], (it & 1) ^ 1, 0x500 | kb);
-            uint8_t* blk = smem_a + kb * kABlockBytes;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
                 const uint32_t off = sw128_offset((uint32_t)(rg + 32 * i), (uint32_t)c);
-                *reinterpret_cast<uint4*>(blk + off) = o[i];
+                *reinterpret_cast<uint4*>(blk + off) = o;
                 if (ModeTraits<MODE>::grad) {
                     uint8_t* img = reinterpret_cast<uint8_t*>(p.J_img) + ((size_t)(tile - p.tile_begin) * KB + kb) * kABlockBytes;
-                    *reinterpret_cast<uint4*>(img + off) = o[i];
+                    *reinterpret_cast<uint4*>(img + off) = o;
                 }
+            }
+            if (kb + 2 < KB) {  // refill this register set with the k-block after next
+                ev = __ldg(ep + (kb + 2) * 8);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dv[i] = __ldg(dp[i] + (kb + 2) * 8);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[kb]);
+        };
+#pragma unroll 1
+        for (int kb = 0; kb < KB; kb += 2) {
+            produce_block(kb, evA, dvA);
+            if (kb + 1 < KB) produce_block(kb + 1, evB, dvB);
         }
         ++it;
     }
