@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TSASR_ABI_VERSION 3
+#define TSASR_ABI_VERSION 4
 
 enum {
     TSASR_OK = 0,
@@ -114,13 +114,17 @@ int tsasr_joint_fwd(const void* enc, const void* dec, const void* W, const float
  *     preparation kernel writes {max T_b, max labels, min T_b, min labels} there, a system-scope fence, then
  *     stats_host[4] = stats_seq -- the caller polls the tag and performs torchaudio's argument checks without a stream,
  *     event or copy of its own (the kernels clamp every length, so nothing depends on the outcome);
- *   cost3: 3*B floats {cost[b] = -log P, ll_alpha[b], ll_beta[b]}. */
+ *   cost3: 3*B floats {cost[b] = -log P, ll_alpha[b], ll_beta[b]};
+ *   enc_bf16 / dec_bf16 (may be NULL; only with operand_dtype == TSASR_F32): bf16 copies of enc / dec that already exist --
+ *     the second output of tsasr_linear_fwd (encoder_proj / decoder_proj) -- used as they are instead of converting that
+ *     operand again; W is still converted. */
 int tsasr_joint_loss_fwd_layout(int B, int T, int U, int H, int V, size_t* offsets8);
 int tsasr_joint_loss_fwd(const void* enc, const void* dec, const void* W, int operand_dtype, const float* bias, const void* targets,
                          int targets_i64, const float* rel_logit_lengths, const float* rel_target_lengths,
                          const int32_t* abs_logit_lengths, const int32_t* abs_target_lengths, int B, int T, int U, int H, int V,
                          int blank, int act_kind, float act_param, void* scratch, size_t scratch_bytes, int32_t* stats_host,
-                         int stats_seq, float* lat2, float* logz, float* alpha, float* beta, float* cost3, tsasr_stream_t stream);
+                         int stats_seq, float* lat2, float* logz, float* alpha, float* beta, float* cost3, const void* enc_bf16,
+                         const void* dec_bf16, tsasr_stream_t stream);
 
 /* Workspace (bytes) tsasr_joint_bwd needs; bounded independently of B*T*U by `max_chunk_cells`
  * (0 = library default). */
@@ -157,6 +161,24 @@ int tsasr_prepare_lengths(const float* rel_logit_lengths, const float* rel_targe
 /* fp32 -> bf16 (round to nearest even) of the three GEMM operands in one launch; counts are in elements. */
 int tsasr_cast_operands_bf16(const float* enc, size_t n_enc, const float* dec, size_t n_dec, const float* W, size_t n_w,
                              void* enc16, void* dec16, void* W16, tsasr_stream_t stream);
+
+/* ---- the projections either side of the joint -------------------------------------
+ * Replaces speechbrain.nnet.linear.Linear.forward (SB/nnet/linear.py:63-76) as instantiated for encoder_proj / decoder_proj
+ * (hparams/LibriSpeechMix/conformer-t_scratch.yaml:172-174,187-189; train_librispeechmix_scratch.py:122,127) and the
+ * autograd backward of nn.Linear.  Row-major fp32 everywhere: X [R,K], W [N,K], bias [N] or NULL, Y [R,N].
+ * tcgen05 GEMMs on in-kernel bf16 (hi, lo) splits of the fp32 operands (3 MMAs per step): fp32-class results
+ * (~1e-6 relative), no operand copies.
+ *   tsasr_linear_fwd: Y = X W^T + bias written as fp32 (Y, may be NULL) and/or bf16 (Y_bf16, may be NULL: the operand
+ *     image tsasr_joint_loss_fwd takes as enc_bf16 / dec_bf16) in the same pass.
+ *   tsasr_linear_bwd: dX = dY W (skipped when dX is NULL), dW = dY^T X and db = column sums of dY (db may be NULL; dW may
+ *     be NULL only together with db), all overwritten; dY is the fp32 d_enc / d_dec of tsasr_joint_bwd, consumed as it is.
+ *     workspace: tsasr_linear_bwd_workspace_bytes(R,K,N) bytes, 256-byte aligned (split-K partials, folded in a fixed
+ *     order: deterministic). */
+size_t tsasr_linear_bwd_workspace_bytes(int R, int K, int N);
+int tsasr_linear_fwd(const float* X, const float* W, const float* bias, int R, int K, int N, float* Y, void* Y_bf16,
+                     tsasr_stream_t stream);
+int tsasr_linear_bwd(const float* dY, const float* X, const float* W, int R, int K, int N, float* dX, float* dW, float* db,
+                     void* workspace, size_t workspace_bytes, tsasr_stream_t stream);
 
 /* ---- decode-time joint step (greedy / beam search) ------------------------------------------------
  * Replaces TransducerBeamSearcher._joint_forward_step (SB/decoders/transducer.py:375-384): Transducer_joint

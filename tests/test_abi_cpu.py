@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/tsasr_b200.h but not exported"
     assert set(declared) == set(_lib.SIGNATURES), "ctypes binding and header disagree"
-    assert _lib.load().tsasr_abi_version() == _lib.ABI_VERSION == 3
+    assert _lib.load().tsasr_abi_version() == _lib.ABI_VERSION == 4
     assert _lib.load().tsasr_lattice_elems(2, 5, 3) == 2 * 7 * 3
 
 
@@ -162,3 +162,36 @@ def test_deferred_finite_check_keeps_the_reference_bookkeeping():
     assert len(b.calls) == 2 and chk.deferred_steps == 0
     tsasr_b200.monitor.uninstall(b)
     assert b.check_gradients.__func__ is Brain.check_gradients
+
+
+def test_linear_dropin_surface_on_cpu():
+    """tsasr_b200.Linear mirrors SB/nnet/linear.py:18-76: same constructor rules and parameter names; on CPU tensors it is
+    the reference's own op (the CUDA kernels have no CPU path)."""
+    with pytest.raises(ValueError, match="Expected one of input_shape or input_size"):
+        tsasr_b200.Linear(4)
+    lin = tsasr_b200.Linear(6, input_shape=[None, None, 5, 3], combine_dims=True)
+    assert lin.w.in_features == 15 and [n for n, _ in lin.named_parameters()] == ["w.weight", "w.bias"]
+    x = torch.randn(2, 7, 5, 3)
+    want = torch.nn.functional.linear(x.reshape(2, 7, 15), lin.w.weight, lin.w.bias)
+    assert torch.equal(lin(x), want)
+    assert tsasr_b200.linear.bf16_twin(want) is None  # CPU tensors never carry a bf16 copy
+    sd = torch.nn.Linear(15, 6).state_dict()
+    lin.w.load_state_dict(sd)  # reference checkpoints (w.weight / w.bias) load unchanged
+
+
+def test_projection_oracle_against_torch():
+    import numpy as np
+    from oracle import projection
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(9, 20, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(7, 20, generator=g, dtype=torch.float64, requires_grad=True)
+    b = torch.randn(7, generator=g, dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.linear(x, w, b)
+    dy = torch.randn(9, 7, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    np.testing.assert_allclose(projection.linear_fwd(x.detach().numpy(), w.detach().numpy(), b.detach().numpy()), y.detach().numpy(), rtol=1e-12)
+    dx, dw, db = projection.linear_bwd(dy.numpy(), x.detach().numpy(), w.detach().numpy())
+    np.testing.assert_allclose(dx, x.grad.numpy(), rtol=1e-12)
+    np.testing.assert_allclose(dw, w.grad.numpy(), rtol=1e-12)
+    np.testing.assert_allclose(db, b.grad.numpy(), rtol=1e-12)

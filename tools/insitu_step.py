@@ -84,8 +84,10 @@ def build_modules(sb, ConformerEncoder, V, dropin, dropout=0.1):
         import tsasr_b200
 
         joint_cls = tsasr_b200.Transducer_joint                     # yaml:191-193, tag swapped
+        proj_cls = tsasr_b200.Linear                                # yaml:172-174,187-189 (N1): bf16 operand producers
     else:
         from speechbrain.nnet.transducer.transducer_joint import Transducer_joint as joint_cls
+        proj_cls = Linear
     d_model, joint_dim = 256, 640
 
     def frontend(padding):
@@ -99,10 +101,10 @@ def build_modules(sb, ConformerEncoder, V, dropin, dropout=0.1):
         "encoder": ConformerEncoder(input_size=2560, d_model=d_model, nhead=4, num_layers=12, d_ffn=2048, dropout=dropout,
                                     activation=torch.nn.LeakyReLU, kernel_size=31, causal=True, injection_mode="cat",
                                     injection_after=0),
-        "encoder_proj": Linear(input_size=d_model, n_neurons=joint_dim),
+        "encoder_proj": proj_cls(input_size=d_model, n_neurons=joint_dim),
         "embedding": Embedding(num_embeddings=V, consider_as_one_hot=True, blank_id=0),
         "decoder": LSTM(input_shape=[None, None, V - 1], hidden_size=512, num_layers=1),
-        "decoder_proj": Linear(input_size=512, n_neurons=joint_dim),
+        "decoder_proj": proj_cls(input_size=512, n_neurons=joint_dim),
         "joiner": joint_cls(joint="sum", nonlinearity=torch.nn.LeakyReLU),
         "transducer_head": Linear(input_size=joint_dim, n_neurons=V),   # stays the stock class in both arms
         "speaker_feature_extractor": Fbank(sample_rate=16000, n_fft=512, n_mels=80, win_length=32),

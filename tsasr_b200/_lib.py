@@ -9,7 +9,7 @@ from . import _build
 
 _lib = None
 
-ABI_VERSION = 3  # TSASR_ABI_VERSION of include/tsasr_b200.h
+ABI_VERSION = 4  # TSASR_ABI_VERSION of include/tsasr_b200.h
 E_INVALID, E_UNSUPPORTED, E_CUDA, E_WORKSPACE = -1, -2, -3, -4
 F32, F16, BF16 = 0, 1, 2
 ACT_CODES = {"leaky_relu": 0, "relu": 1, "tanh": 2, "identity": 3}
@@ -29,7 +29,10 @@ SIGNATURES = {
     "tsasr_joint_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "tsasr_joint_loss_fwd_layout": (_i, [_i, _i, _i, _i, _i, _vp]),
     "tsasr_joint_loss_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _sz,
-                                  _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                  _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tsasr_linear_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tsasr_linear_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "tsasr_linear_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "tsasr_joint_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _ll]),
     "tsasr_joint_bwd_stats_offset": (_sz, [_i, _i, _i, _i, _i, _ll]),
     "tsasr_joint_bwd": (_i, [_vp] * 7 + [_i] * 7 + [_f] + [_vp] * 7 + [_sz, _ll, _f, _f] + [_vp] * 5),

@@ -19,6 +19,7 @@
 #include "backward_gemm.cuh"
 #include "common.cuh"
 #include "joint_gemm.cuh"
+#include "linear.cuh"
 
 namespace tsasr {
 // lattice.cu
@@ -463,7 +464,8 @@ int tsasr_joint_loss_fwd(const void* enc, const void* dec, const void* W, int op
                          int targets_i64, const float* rel_logit_lengths, const float* rel_target_lengths,
                          const int32_t* abs_logit_lengths, const int32_t* abs_target_lengths, int B, int T, int U, int H, int V,
                          int blank, int act_kind, float act_param, void* scratch, size_t scratch_bytes, int32_t* stats_host,
-                         int stats_seq, float* lat2, float* logz, float* alpha, float* beta, float* cost3, tsasr_stream_t stream) {
+                         int stats_seq, float* lat2, float* logz, float* alpha, float* beta, float* cost3, const void* enc_bf16,
+                         const void* dec_bf16, tsasr_stream_t stream) {
     NvtxRange nvtx_range("tsasr_joint_loss_fwd");
     if (int rc = check_dims(B, T, U, V, blank)) return rc;
     REQUIRE(enc && dec && W && bias && scratch && lat2 && logz && alpha && beta && cost3, "null pointer argument");
@@ -480,8 +482,11 @@ int tsasr_joint_loss_fwd(const void* enc, const void* dec, const void* W, int op
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint8_t* sc = static_cast<uint8_t*>(scratch);
     const bool cast = operand_dtype == TSASR_F32;
-    const void* enc16 = cast ? sc + off[0] : enc;
-    const void* dec16 = cast ? sc + off[1] : dec;
+    REQUIRE(cast || (!enc_bf16 && !dec_bf16), "enc_bf16 / dec_bf16 accompany fp32 operands only");
+    // an operand whose bf16 copy already exists (tsasr_linear_fwd's second output) is not converted again
+    const bool cast_enc = cast && !enc_bf16, cast_dec = cast && !dec_bf16;
+    const void* enc16 = cast_enc ? sc + off[0] : (cast ? enc_bf16 : enc);
+    const void* dec16 = cast_dec ? sc + off[1] : (cast ? dec_bf16 : dec);
     const void* W16 = cast ? sc + off[2] : W;
     const int32_t* tg32 = targets_i64 ? reinterpret_cast<const int32_t*>(sc + off[3]) : static_cast<const int32_t*>(targets);
     int32_t* ll = reinterpret_cast<int32_t*>(sc + off[4]);
@@ -504,8 +509,8 @@ int tsasr_joint_loss_fwd(const void* enc, const void* dec, const void* W, int op
     {
         ScopedTiming tm("prepare_inputs_kernel", st);
         cudaError_t e = launch_prepare_inputs(
-            cast ? static_cast<const float*>(enc) : nullptr, cast ? (size_t)B * T * H : 0, cast ? static_cast<const float*>(dec) : nullptr,
-            cast ? (size_t)B * U * H : 0, cast ? static_cast<const float*>(W) : nullptr, cast ? (size_t)V * H : 0, sc + off[0], sc + off[1],
+            cast_enc ? static_cast<const float*>(enc) : nullptr, cast_enc ? (size_t)B * T * H : 0, cast_dec ? static_cast<const float*>(dec) : nullptr,
+            cast_dec ? (size_t)B * U * H : 0, cast ? static_cast<const float*>(W) : nullptr, cast ? (size_t)V * H : 0, sc + off[0], sc + off[1],
             sc + off[2], targets_i64 ? static_cast<const long long*>(targets) : nullptr, (size_t)B * (U - 1),
             reinterpret_cast<int*>(sc + off[3]), rel_logit_lengths, rel_target_lengths, abs_logit_lengths, abs_target_lengths, B, T, U - 1,
             ll, tl, stats, stats_dev, stats_seq, sms, st);
@@ -610,3 +615,4 @@ int tsasr_joint_debug_logits(const void* enc, const void* dec, const void* W, co
 }  // extern "C"
 
 #include "backward_capi.inl"
+#include "linear_capi.inl"

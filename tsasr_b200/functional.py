@@ -331,6 +331,13 @@ class FusedJointRnnt(torch.autograd.Function):
                          for t in ops_)
             code = _lib.BF16
         Hp = ops_[0].shape[-1]
+        # projections that ran through tsasr_linear_fwd (tsasr_b200.Linear) left the bf16 rounding of their output behind:
+        # it IS the operand image, so the preparation kernel skips that operand
+        tw_enc = tw_dec = None
+        if code == _lib.F32:
+            from .linear import bf16_twin
+
+            tw_enc, tw_dec = bf16_twin(enc), bf16_twin(dec)
         b32 = bias.detach()
         if b32.dtype != torch.float32 or not b32.is_contiguous():
             b32 = b32.to(torch.float32).contiguous()
@@ -358,10 +365,11 @@ class FusedJointRnnt(torch.autograd.Function):
                 ops_[0].data_ptr(), ops_[1].data_ptr(), ops_[2].data_ptr(), code, b32.data_ptr(), tg.data_ptr() if tg.numel() else None,
                 1 if tg.dtype == torch.int64 else 0, *len_args, B, T, U, Hp, V, int(blank), int(act_kind), float(act_param),
                 scratch.data_ptr(), scratch.numel(), slot_ptr, seq, lat2.data_ptr(), logz.data_ptr(), alpha.data_ptr(), beta.data_ptr(),
-                cost3.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+                cost3.data_ptr(), tw_enc.data_ptr() if tw_enc is not None else None, tw_dec.data_ptr() if tw_dec is not None else None,
+                torch.cuda.current_stream(dev).cuda_stream))
         if code == _lib.F32:
-            enc16 = scratch[off[0]: off[0] + 2 * B * T * Hp].view(torch.bfloat16).view(B, T, Hp)
-            dec16 = scratch[off[1]: off[1] + 2 * B * U * Hp].view(torch.bfloat16).view(B, U, Hp)
+            enc16 = tw_enc if tw_enc is not None else scratch[off[0]: off[0] + 2 * B * T * Hp].view(torch.bfloat16).view(B, T, Hp)
+            dec16 = tw_dec if tw_dec is not None else scratch[off[1]: off[1] + 2 * B * U * Hp].view(torch.bfloat16).view(B, U, Hp)
             W16 = scratch[off[2]: off[2] + 2 * V * Hp].view(torch.bfloat16).view(V, Hp)
         else:
             enc16, dec16, W16 = ops_
