@@ -166,8 +166,8 @@ int tsasr_cast_operands_bf16(const float* enc, size_t n_enc, const float* dec, s
  * Replaces speechbrain.nnet.linear.Linear.forward (SB/nnet/linear.py:63-76) as instantiated for encoder_proj / decoder_proj
  * (hparams/LibriSpeechMix/conformer-t_scratch.yaml:172-174,187-189; train_librispeechmix_scratch.py:122,127) and the
  * autograd backward of nn.Linear.  Row-major fp32 everywhere: X [R,K], W [N,K], bias [N] or NULL, Y [R,N].
- * tcgen05 GEMMs on in-kernel bf16 (hi, lo) splits of the fp32 operands (3 MMAs per step): fp32-class results
- * (~1e-6 relative), no operand copies.
+ * tcgen05 GEMMs on in-kernel bf16 (hi, lo) splits of the fp32 operands (3 MMAs per step): 16-17 bits per term
+ * (max error ~1e-5 of the largest output at K = 256), no operand copies.
  *   tsasr_linear_fwd: Y = X W^T + bias written as fp32 (Y, may be NULL) and/or bf16 (Y_bf16, may be NULL: the operand
  *     image tsasr_joint_loss_fwd takes as enc_bf16 / dec_bf16) in the same pass.
  *   tsasr_linear_bwd: dX = dY W (skipped when dX is NULL), dW = dY^T X and db = column sums of dY (db may be NULL; dW may
@@ -179,6 +179,66 @@ int tsasr_linear_fwd(const float* X, const float* W, const float* bias, int R, i
                      tsasr_stream_t stream);
 int tsasr_linear_bwd(const float* dY, const float* X, const float* W, int R, int K, int N, float* dX, float* dW, float* db,
                      void* workspace, size_t workspace_bytes, tsasr_stream_t stream);
+
+/* ---- the prediction network ---------------------------------------------------------
+ * Replaces speechbrain.nnet.embedding.Embedding(consider_as_one_hot=True) (SB/nnet/embedding.py:65-114) followed by
+ * speechbrain.nnet.RNN.LSTM (one layer, unidirectional; SB/nnet/RNN.py:170-278, torch.nn.LSTM on a PackedSequence) as
+ * chained at train_librispeechmix_scratch.py:125-126 (hparams/LibriSpeechMix/conformer-t_scratch.yaml:176-185).
+ * fp32 arithmetic throughout (gate order i, f, g, o; h_0 = c_0 = 0).
+ *   tsasr_lstm_fwd: the whole teacher-forced recurrence in one cooperative launch.
+ *     input: EITHER tokens [B,U] (int32, or int64 when tokens_i64 != 0) + W_ih [4Hd, n_embed]: the one-hot embedding of
+ *       token k is column k - [k > blank] of W_ih (nothing for k == blank), gathered -- no [B,U,V-1] tensor, no GEMM;
+ *       OR xw [B,U,4Hd] = x W_ih^T + b_ih precomputed (tsasr_linear_fwd) for a dense input.
+ *     lengths: rel_lengths fp32 (SpeechBrain relative; converted as SB/nnet/RNN.py:35 + pack_padded_sequence do: fp32
+ *       product, truncation) or abs_lengths int32; positions u >= length read as zeros in `out` and freeze the state.
+ *     out [B,U,Hd]; optional (NULL to skip): hprev [B,U,Hd] = h_{u-1}, gates [B,U,4,Hd] (activated), cells [B,U,Hd]
+ *       (what tsasr_lstm_bwd needs), h_n / c_n [B,Hd], lengths_out [B] int32.
+ *     Hd in {128, 256, 512}, B <= 64; else TSASR_E_UNSUPPORTED.
+ *   tsasr_lstm_bwd: back-propagation through time in one cooperative launch; d_out [B,U,Hd] (+ optional d_hn, d_cn [B,Hd])
+ *     -> dG [B,U,4Hd] = gradient w.r.t. the gate pre-activations (zeros at padded positions).  From it:
+ *       dW_hh = dG^T hprev and db_ih = db_hh = column sums of dG: tsasr_linear_bwd(dG, hprev, NULL, B*U, Hd, 4Hd, NULL, dW_hh, db);
+ *       dW_ih: tsasr_onehot_dw (one-hot input; deterministic gather-sum) or tsasr_linear_bwd against the dense input.
+ *   workspace: tsasr_lstm_workspace_bytes(U) bytes, 16-byte aligned (per-step arrival counters; zeroed by the call). */
+size_t tsasr_lstm_workspace_bytes(int U);
+int tsasr_lstm_fwd(const void* tokens, int tokens_i64, int blank, int n_embed, const float* xw, const float* W_ih, const float* W_hh,
+                   const float* b_ih, const float* b_hh, const float* rel_lengths, const int32_t* abs_lengths, int B, int U, int Hd,
+                   float* out, float* hprev, float* gates, float* cells, float* h_n, float* c_n, int32_t* lengths_out,
+                   void* workspace, size_t workspace_bytes, tsasr_stream_t stream);
+int tsasr_lstm_bwd(const float* d_out, const float* d_hn, const float* d_cn, const float* W_hh, const float* gates, const float* cells,
+                   const int32_t* lengths, int B, int U, int Hd, float* dG, void* workspace, size_t workspace_bytes,
+                   tsasr_stream_t stream);
+int tsasr_onehot_dw(const void* tokens, int tokens_i64, int blank, int n_embed, const float* dG, int n_pos, int G, float* dW_ih,
+                    tsasr_stream_t stream);
+
+/* ---- the prediction network ---------------------------------------------------------
+ * Replaces speechbrain.nnet.embedding.Embedding(consider_as_one_hot=True) (SB/nnet/embedding.py:65-114) followed by
+ * speechbrain.nnet.RNN.LSTM (one layer, unidirectional; SB/nnet/RNN.py:170-278, torch.nn.LSTM on a PackedSequence) as
+ * chained at train_librispeechmix_scratch.py:125-126 (hparams/LibriSpeechMix/conformer-t_scratch.yaml:176-185).
+ * fp32 arithmetic throughout (gate order i, f, g, o; h_0 = c_0 = 0).
+ *   tsasr_lstm_fwd: the whole teacher-forced recurrence in one cooperative launch.
+ *     input: EITHER tokens [B,U] (int32, or int64 when tokens_i64 != 0) + W_ih [4Hd, n_embed]: the one-hot embedding of
+ *       token k is column k - [k > blank] of W_ih (nothing for k == blank), gathered -- no [B,U,V-1] tensor, no GEMM;
+ *       OR xw [B,U,4Hd] = x W_ih^T + b_ih precomputed (tsasr_linear_fwd) for a dense input.
+ *     lengths: rel_lengths fp32 (SpeechBrain relative; converted as SB/nnet/RNN.py:35 + pack_padded_sequence do: fp32
+ *       product, truncation) or abs_lengths int32; positions u >= length read as zeros in `out` and freeze the state.
+ *     out [B,U,Hd]; optional (NULL to skip): hprev [B,U,Hd] = h_{u-1}, gates [B,U,4,Hd] (activated), cells [B,U,Hd]
+ *       (what tsasr_lstm_bwd needs), h_n / c_n [B,Hd], lengths_out [B] int32.
+ *     Hd in {128, 256, 512}, B <= 64; else TSASR_E_UNSUPPORTED.
+ *   tsasr_lstm_bwd: back-propagation through time in one cooperative launch; d_out [B,U,Hd] (+ optional d_hn, d_cn [B,Hd])
+ *     -> dG [B,U,4Hd] = gradient w.r.t. the gate pre-activations (zeros at padded positions).  From it:
+ *       dW_hh = dG^T hprev and db_ih = db_hh = column sums of dG: tsasr_linear_bwd(dG, hprev, NULL, B*U, Hd, 4Hd, NULL, dW_hh, db);
+ *       dW_ih: tsasr_onehot_dw (one-hot input; deterministic gather-sum) or tsasr_linear_bwd against the dense input.
+ *   workspace: tsasr_lstm_workspace_bytes(U) bytes, 16-byte aligned (per-step arrival counters; zeroed by the call). */
+size_t tsasr_lstm_workspace_bytes(int U);
+int tsasr_lstm_fwd(const void* tokens, int tokens_i64, int blank, int n_embed, const float* xw, const float* W_ih, const float* W_hh,
+                   const float* b_ih, const float* b_hh, const float* rel_lengths, const int32_t* abs_lengths, int B, int U, int Hd,
+                   float* out, float* hprev, float* gates, float* cells, float* h_n, float* c_n, int32_t* lengths_out,
+                   void* workspace, size_t workspace_bytes, tsasr_stream_t stream);
+int tsasr_lstm_bwd(const float* d_out, const float* d_hn, const float* d_cn, const float* W_hh, const float* gates, const float* cells,
+                   const int32_t* lengths, int B, int U, int Hd, float* dG, void* workspace, size_t workspace_bytes,
+                   tsasr_stream_t stream);
+int tsasr_onehot_dw(const void* tokens, int tokens_i64, int blank, int n_embed, const float* dG, int n_pos, int G, float* dW_ih,
+                    tsasr_stream_t stream);
 
 /* ---- decode-time joint step (greedy / beam search) ------------------------------------------------
  * Replaces TransducerBeamSearcher._joint_forward_step (SB/decoders/transducer.py:375-384): Transducer_joint

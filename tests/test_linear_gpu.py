@@ -1,10 +1,10 @@
 """GPU parity tests of the projection GEMMs (encoder_proj / decoder_proj) through the C ABI.
 
 Oracle: oracle/projection.py (float64 restatement of SB/nnet/linear.py:74 and its autograd backward).  The kernels run on
-the bf16 tensor cores with an in-kernel (hi, lo) split of the fp32 operands; the bar is fp32-class accuracy: every element
-within 1.2e-5 * sum_k |x_k||w_k| of the exact value -- the worst case of the split (3 * 2^-18 per term: the dropped lo*lo
-product and the rounding of each lo part), reached only when every term errs the same way (K = 7 case below: 0.95 of
-it); at the recipe's K = 256 / 512 the measured worst element is 0.2 of the bound and 1.4e-5 of the largest output."""
+the bf16 tensor cores with an in-kernel (hi, lo) split of the fp32 operands; the bar is the split's own worst case, elementwise:
+4.6e-5 * sum_k |x_k||w_k| (3 * 2^-16 per term: the dropped lo*lo product and the rounding of each lo part; reached only when
+every term errs the same way -- a K = 3 contraction measured 0.3 of it), plus, at every shape, a max error below 3e-5 of the
+largest output (measured 1.4e-5 at the recipe's K = 256; plain bf16 operands would give 4e-3)."""
 import numpy as np
 import pytest
 import torch
@@ -14,7 +14,7 @@ from tsasr_b200 import _lib, linear as tlin
 from oracle import projection as oracle
 
 pytestmark = pytest.mark.gpu
-REL = 1.3e-5
+REL = 4.6e-5
 
 
 def _dev():

@@ -137,3 +137,26 @@ def test_config1_c_oracle_vs_torchaudio():
     costs, grads = rnnt_c.rnnt_torchaudio(logits.numpy(), targets.numpy(), ll.numpy(), tl.numpy(), 0)
     np.testing.assert_allclose(costs, c.detach().numpy(), rtol=1e-5)
     assert np.abs(grads - t.grad.numpy()).max() < 1e-4
+
+
+# ---- prediction network: the restatement against the reference's own modules ----
+PREDICTOR_GOLDEN = ["predictor_onehot_ragged", "predictor_onehot_blank3", "predictor_onehot_full", "predictor_dense"]
+
+
+@pytest.mark.parametrize("name", PREDICTOR_GOLDEN)
+def test_predictor_oracle_matches_reference_modules(golden, name):
+    """oracle/predictor.py (explicit float64 loops) against the outputs and gradients of speechbrain's Embedding + LSTM
+    (oracle/make_golden_predictor.py ran the REAL modules of /root/reference): pins the one-hot column mapping incl.
+    blank != 0, the gate order, the packed-sequence semantics and the TRUNCATING length conversion of the packing."""
+    from oracle import predictor
+
+    g = golden(name)
+    params = {k: torch.from_numpy(g[k]) for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")}
+    rel = torch.from_numpy(g["rel_lengths"]) if g["rel_lengths"].size else None
+    dense = torch.from_numpy(g["x"]) if "x" in g else None
+    res = predictor.predictor_fwd_bwd(torch.from_numpy(g["tokens"]), int(g["vocab"]), int(g["blank"]), params, rel,
+                                      torch.from_numpy(g["d_out"]), x_dense=dense)
+    if name == "predictor_onehot_ragged":
+        assert res["lengths"].tolist() == [13, 7, 3, 7, 1]  # 0.6 * 13 = 7.8 is truncated (the loss would round it to 8)
+    for key in ("out", "h_n", "c_n", "d_weight_ih", "d_weight_hh", "d_bias_ih", "d_bias_hh") + (("d_x",) if dense is not None else ()):
+        np.testing.assert_allclose(res[key].numpy(), g[key], rtol=2e-4, atol=2e-6, err_msg=key)

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.environ.get("TSASR_B200_LIB") or os.path.join(_HERE, "libtsasr_b200.so")  # env override: A/B runs of two builds
-SOURCES = ["capi.cu", "lattice.cu", "decode.cu", "prep.cu"]
+SOURCES = ["capi.cu", "lattice.cu", "decode.cu", "prep.cu", "predictor.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "joint_gemm.cuh"
 #include "linear.cuh"
+#include "predictor.cuh"
 
 namespace tsasr {
 // lattice.cu
@@ -616,3 +617,4 @@ int tsasr_joint_debug_logits(const void* enc, const void* dec, const void* W, co
 
 #include "backward_capi.inl"
 #include "linear_capi.inl"
+#include "predictor_capi.inl"

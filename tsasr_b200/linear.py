@@ -5,8 +5,8 @@ in ``self.w`` so checkpoints keep their ``w.weight`` / ``w.bias`` names) as the 
 ``encoder_proj`` and ``decoder_proj`` (hparams/LibriSpeechMix/conformer-t_scratch.yaml:172-174,187-189; called at
 train_librispeechmix_scratch.py:122,127).
 
-On CUDA fp32 inputs the product runs in ``tsasr_linear_fwd`` (tcgen05 GEMM on in-kernel bf16 hi/lo splits: fp32-class
-result) whose epilogue writes the fp32 output AND its bf16 rounding.  The bf16 copy is remembered here, keyed by the
+On CUDA fp32 inputs the product runs in ``tsasr_linear_fwd`` (tcgen05 GEMM on in-kernel bf16 hi/lo splits: 16-17 bits
+per term) whose epilogue writes the fp32 output AND its bf16 rounding.  The bf16 copy is remembered here, keyed by the
 output's storage, and ``FusedJointRnnt`` picks it up as the joint GEMM's operand image: the fp32 -> bf16 pass over
 ``enc_out`` / ``dec_out`` inside the fused loss disappears, and the backward (``tsasr_linear_bwd``) consumes the fp32
 ``d_enc`` / ``d_dec`` of the joint backward as they are.  A ``JointHandle`` input (this class used as the transducer
