@@ -198,15 +198,14 @@ int tsasr_linear_bwd(const float* dY, const float* X, const float* W, int R, int
  *     -> dG [B,U,4Hd] = gradient w.r.t. the gate pre-activations (zeros at padded positions).  From it:
  *       dW_hh = dG^T hprev and db_ih = db_hh = column sums of dG: tsasr_linear_bwd(dG, hprev, NULL, B*U, Hd, 4Hd, NULL, dW_hh, db);
  *       dW_ih: tsasr_onehot_dw (one-hot input; deterministic gather-sum) or tsasr_linear_bwd against the dense input.
- *   workspace: tsasr_lstm_workspace_bytes(U) bytes, 16-byte aligned (per-step arrival counters; zeroed by the call). */
-size_t tsasr_lstm_workspace_bytes(int U);
+ *   Both launches hand a step's results from CTA to CTA through `out` / `dG` themselves (pre-filled with a sentinel by the
+ *   call, polled by the consumers): no workspace, no flags. */
 int tsasr_lstm_fwd(const void* tokens, int tokens_i64, int blank, int n_embed, const float* xw, const float* W_ih, const float* W_hh,
                    const float* b_ih, const float* b_hh, const float* rel_lengths, const int32_t* abs_lengths, int B, int U, int Hd,
                    float* out, float* hprev, float* gates, float* cells, float* h_n, float* c_n, int32_t* lengths_out,
-                   void* workspace, size_t workspace_bytes, tsasr_stream_t stream);
-int tsasr_lstm_bwd(const float* d_out, const float* d_hn, const float* d_cn, const float* W_hh, const float* gates, const float* cells,
-                   const int32_t* lengths, int B, int U, int Hd, float* dG, void* workspace, size_t workspace_bytes,
                    tsasr_stream_t stream);
+int tsasr_lstm_bwd(const float* d_out, const float* d_hn, const float* d_cn, const float* W_hh, const float* gates, const float* cells,
+                   const int32_t* lengths, int B, int U, int Hd, float* dG, tsasr_stream_t stream);
 int tsasr_onehot_dw(const void* tokens, int tokens_i64, int blank, int n_embed, const float* dG, int n_pos, int G, float* dW_ih,
                     tsasr_stream_t stream);
 
@@ -228,15 +227,14 @@ int tsasr_onehot_dw(const void* tokens, int tokens_i64, int blank, int n_embed, 
  *     -> dG [B,U,4Hd] = gradient w.r.t. the gate pre-activations (zeros at padded positions).  From it:
  *       dW_hh = dG^T hprev and db_ih = db_hh = column sums of dG: tsasr_linear_bwd(dG, hprev, NULL, B*U, Hd, 4Hd, NULL, dW_hh, db);
  *       dW_ih: tsasr_onehot_dw (one-hot input; deterministic gather-sum) or tsasr_linear_bwd against the dense input.
- *   workspace: tsasr_lstm_workspace_bytes(U) bytes, 16-byte aligned (per-step arrival counters; zeroed by the call). */
-size_t tsasr_lstm_workspace_bytes(int U);
+ *   Both launches hand a step's results from CTA to CTA through `out` / `dG` themselves (pre-filled with a sentinel by the
+ *   call, polled by the consumers): no workspace, no flags. */
 int tsasr_lstm_fwd(const void* tokens, int tokens_i64, int blank, int n_embed, const float* xw, const float* W_ih, const float* W_hh,
                    const float* b_ih, const float* b_hh, const float* rel_lengths, const int32_t* abs_lengths, int B, int U, int Hd,
                    float* out, float* hprev, float* gates, float* cells, float* h_n, float* c_n, int32_t* lengths_out,
-                   void* workspace, size_t workspace_bytes, tsasr_stream_t stream);
-int tsasr_lstm_bwd(const float* d_out, const float* d_hn, const float* d_cn, const float* W_hh, const float* gates, const float* cells,
-                   const int32_t* lengths, int B, int U, int Hd, float* dG, void* workspace, size_t workspace_bytes,
                    tsasr_stream_t stream);
+int tsasr_lstm_bwd(const float* d_out, const float* d_hn, const float* d_cn, const float* W_hh, const float* gates, const float* cells,
+                   const int32_t* lengths, int B, int U, int Hd, float* dG, tsasr_stream_t stream);
 int tsasr_onehot_dw(const void* tokens, int tokens_i64, int blank, int n_embed, const float* dG, int n_pos, int G, float* dW_ih,
                     tsasr_stream_t stream);
 

@@ -1,6 +1,6 @@
 """BASELINE configs[4] in situ: one accumulation cycle of the REAL ``TSASR.fit_batch`` (train_librispeechmix_scratch.py:33-190,
-SB/core.py:1032-1096) with the drop-in ``Transducer_joint`` / ``transducer_loss`` against the same cycle with the stock
-SpeechBrain modules -- same initial weights, same synthetic batch, same dropout seeds.  Needs the reference install under
+SB/core.py:1032-1096) with every drop-in (``Transducer_joint`` / ``transducer_loss``, the projection ``Linear``s, the prediction
+network's ``Embedding`` / ``LSTM``) against the same cycle with the stock SpeechBrain modules -- same initial weights, same synthetic batch, same dropout seeds.  Needs the reference install under
 baseline/_ref (tools/install_reference.sh, travels to the GPU box); skipped when it is absent."""
 import os
 import sys
@@ -36,6 +36,8 @@ def test_one_fit_batch_cycle_matches_the_stock_recipe():
         assert brain.optimizer_step == 1                       # the cycle ended with an optimizer step
         if dropin:
             assert isinstance(brain.modules.joiner, tsasr_b200.Transducer_joint)
+            assert isinstance(getattr(brain.modules.decoder, "module", brain.modules.decoder), tsasr_b200.LSTM)
+            assert isinstance(getattr(brain.modules.encoder_proj, "module", brain.modules.encoder_proj), tsasr_b200.Linear)
             assert tsasr_b200._lib.launch_count() > launches0  # the fused kernels ran inside fit_batch
         else:
             assert tsasr_b200._lib.launch_count() == launches0
@@ -46,3 +48,4 @@ def test_one_fit_batch_cycle_matches_the_stock_recipe():
     assert par["loss_rel_err_max"] < 1e-4, par
     assert par["head_grad_max_err_over_max"] < 1e-2 and par["head_bias_grad_max_err_over_max"] < 1e-2, par
     assert par["enc_proj_grad_max_err_over_max"] < 2e-2, par
+    assert par["dec_rnn_hh_grad_max_err_over_max"] < 2e-2 and par["dec_rnn_ih_grad_max_err_over_max"] < 2e-2, par

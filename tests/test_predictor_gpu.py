@@ -118,10 +118,9 @@ def test_predictor_lengths_truncate_like_the_reference_packing():
     tokens = torch.zeros((B, U), dtype=torch.int32, device=d)
     W_ih, W_hh = torch.zeros(4 * Hd, V - 1, device=d), torch.zeros(4 * Hd, Hd, device=d)
     out, L = torch.empty(B, U, Hd, device=d), torch.empty(B, dtype=torch.int32, device=d)
-    ws = torch.empty(lib.tsasr_lstm_workspace_bytes(U), dtype=torch.uint8, device=d)
     reld = rel.to(d)
     _lib.check(lib.tsasr_lstm_fwd(tokens.data_ptr(), 0, 0, V - 1, None, W_ih.data_ptr(), W_hh.data_ptr(), None, None, reld.data_ptr(), None,
-                                  B, U, Hd, out.data_ptr(), None, None, None, None, None, L.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  B, U, Hd, out.data_ptr(), None, None, None, None, None, L.data_ptr(),
                                   torch.cuda.current_stream(d).cuda_stream))
     torch.cuda.synchronize()
     assert L.cpu().tolist() == oracle.packed_lengths(rel, U).tolist() == (rel * U).to(torch.int64).tolist()

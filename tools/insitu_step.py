@@ -71,7 +71,7 @@ def import_reference():
     return sb, rec, ConformerEncoder
 
 
-def build_modules(sb, ConformerEncoder, V, dropin, dropout=0.1):
+def build_modules(sb, ConformerEncoder, V, dropin, dropout=0.1, which="all"):
     """Module tree of conformer-t_scratch.yaml:122-232 (+ the causal / cat overrides of the SpkEmbCat_Causal task)."""
     from speechbrain.lobes.features import Fbank
     from speechbrain.lobes.models.convolution import ConvolutionFrontEnd
@@ -84,7 +84,11 @@ def build_modules(sb, ConformerEncoder, V, dropin, dropout=0.1):
         import tsasr_b200
 
         joint_cls = tsasr_b200.Transducer_joint                     # yaml:191-193, tag swapped
-        proj_cls = tsasr_b200.Linear                                # yaml:172-174,187-189 (N1): bf16 operand producers
+        proj_cls = Linear
+        if which in ("all", "joint+proj"):
+            proj_cls = tsasr_b200.Linear                            # yaml:172-174,187-189 (N1): bf16 operand producers
+        if which == "all":
+            Embedding, LSTM = tsasr_b200.Embedding, tsasr_b200.LSTM  # yaml:176-185 (N3): the prediction network
     else:
         from speechbrain.nnet.transducer.transducer_joint import Transducer_joint as joint_cls
         proj_cls = Linear
@@ -156,9 +160,10 @@ def make_batch(sb, B, seconds, n_labels, V, seed, ragged=False):
     return PaddedBatch(items)
 
 
-def make_brain(sb, rec, ConformerEncoder, V, dropin, device, distributed, grad_accumulation_factor, seed, dropout, deferred_check=False):
+def make_brain(sb, rec, ConformerEncoder, V, dropin, device, distributed, grad_accumulation_factor, seed, dropout, deferred_check=False,
+               which="all"):
     torch.manual_seed(seed)  # identical initial weights in both arms (and on every rank, as DDP would broadcast them)
-    mods = build_modules(sb, ConformerEncoder, V, dropin, dropout)
+    mods = build_modules(sb, ConformerEncoder, V, dropin, dropout, which)
     hparams = build_hparams(sb, dropin, grad_accumulation_factor)
     rec.hparams = hparams  # TSASR reads the module-global `hparams` for its plot_* switches (:65,98)
     run_opts = {"device": str(device)}
@@ -197,6 +202,9 @@ def parity_cycle(brain, batches, grad_accumulation_factor, seed):
             captured["head_bias_grad"] = w.bias.grad.detach().float().cpu().clone()
             enc_proj = getattr(brain.modules.encoder_proj, "module", brain.modules.encoder_proj)
             captured["enc_proj_grad"] = enc_proj.w.weight.grad.detach().float().cpu().clone()
+            dec = getattr(brain.modules.decoder, "module", brain.modules.decoder)
+            captured["dec_rnn_hh_grad"] = dec.rnn.weight_hh_l0.grad.detach().float().cpu().clone()
+            captured["dec_rnn_ih_grad"] = dec.rnn.weight_ih_l0.grad.detach().float().cpu().clone()
         return orig_step(*a, **k)
 
     brain.optimizer.step = capturing_step
@@ -211,7 +219,7 @@ def parity_cycle(brain, batches, grad_accumulation_factor, seed):
 def run_arm(sb, rec, ConformerEncoder, args, dropin, device, world, deferred_check=False):
     """-> dict(ms_per_step, peak_mem_gib, losses, gradients of the first accumulation cycle)."""
     brain = make_brain(sb, rec, ConformerEncoder, args.vocab, dropin, device, world > 1, args.grad_accumulation_factor, args.seed, args.dropout,
-                       deferred_check)
+                       deferred_check, args.dropins)
     rank = int(os.environ.get("RANK", "0"))
     batches = [make_batch(sb, args.batch, args.seconds, args.labels, args.vocab, seed=1000 * rank + i, ragged=args.ragged)
                for i in range(4)]
@@ -247,7 +255,7 @@ def compare(stock, dropin):
     """Parity line between the two arms (same seeds, same initial weights, same batches)."""
     rel = max(abs(a - b) / max(abs(a), 1e-12) for a, b in zip(stock["losses"], dropin["losses"]))
     out = {"loss_rel_err_max": rel, "losses_stock": stock["losses"], "losses_dropin": dropin["losses"]}
-    for k in ("head_grad", "head_bias_grad", "enc_proj_grad"):
+    for k in ("head_grad", "head_bias_grad", "enc_proj_grad", "dec_rnn_hh_grad", "dec_rnn_ih_grad"):
         a, b = stock[k].double(), dropin[k].double()
         out[k + "_max_err_over_max"] = ((a - b).abs().max() / a.abs().max()).item()
         out[k + "_rel_l2"] = ((a - b).norm() / a.norm()).item()
@@ -267,6 +275,9 @@ def main():
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--ragged", action="store_true")
+    ap.add_argument("--dropins", default="all", choices=["joint", "joint+proj", "all"],
+                    help="which drop-ins the dropin arm uses: the fused joint + loss only (round-2 sessions 1-12), plus the projection "
+                         "GEMMs (N1), plus the prediction network (N3)")
     ap.add_argument("--deferred-check", dest="deferred_check", action="store_true",
                     help="third arm: drop-ins + tsasr_b200.monitor.install(brain) (no loss.isfinite() host sync between forward and backward)")
     args = ap.parse_args()
@@ -292,7 +303,7 @@ def main():
         out = {"what": "full fit_batch of train_librispeechmix_scratch.py TSASR (causal Conformer, injection_mode=cat, V=%d), "
                        "synthetic %.0f s audio, B=%d per GPU, %d labels, grad_accumulation_factor=%d, reference per-module DDP"
                        % (args.vocab, args.seconds, args.batch, args.labels, args.grad_accumulation_factor),
-               "n_gpus": world, "utterances_per_step": cells}
+               "n_gpus": world, "utterances_per_step": cells, "dropins": args.dropins}
         for k, v in res.items():
             out[k] = {kk: vv for kk, vv in v.items() if not isinstance(vv, torch.Tensor)}
         if "stock" in res and "dropin" in res:

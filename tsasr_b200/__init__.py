@@ -7,14 +7,17 @@ Drop-in surface (same names/signatures as the vendored SpeechBrain pieces the re
     tsasr_b200.TransducerLoss/Transducer <- speechbrain.nnet.loss.transducer_loss.{TransducerLoss,Transducer}
     tsasr_b200.Linear                    <- speechbrain.nnet.linear.Linear (encoder_proj / decoder_proj: tcgen05 GEMMs whose
                                             bf16 output copy feeds the fused joint directly)
+    tsasr_b200.Embedding / tsasr_b200.LSTM <- speechbrain.nnet.embedding.Embedding / speechbrain.nnet.RNN.LSTM (the prediction
+                                            network: one-hot gather + the whole recurrence in one cooperative launch)
 
 plus the functional forms ``rnnt_loss`` (torchaudio signature) and ``fused_joint_rnnt_loss``.
 All arithmetic runs in libtsasr_b200.so (hand-written CUDA, C ABI in include/tsasr_b200.h); there
 is no CPU path and no PyTorch fallback for the loss.
 """
-from . import _lib, linear, monitor, ops  # noqa: F401
+from . import _lib, linear, monitor, ops, predictor  # noqa: F401
 from .functional import fused_joint_rnnt_loss, rnnt_loss  # noqa: F401
 from .linear import Linear  # noqa: F401
+from .predictor import Embedding, LSTM, OneHotHandle  # noqa: F401
 from .losses import Transducer, TransducerLoss, transducer_loss  # noqa: F401
 from .transducer_joint import JointHandle, Transducer_joint  # noqa: F401
 

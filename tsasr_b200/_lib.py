@@ -38,13 +38,11 @@ SIGNATURES = {
     "tsasr_joint_bwd": (_i, [_vp] * 7 + [_i] * 7 + [_f] + [_vp] * 7 + [_sz, _ll, _f, _f] + [_vp] * 5),
     "tsasr_prepare_lengths": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "tsasr_cast_operands_bf16": (_i, [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp]),
-    "tsasr_lstm_workspace_bytes": (_sz, [_i]),
-    "tsasr_lstm_fwd": (_i, [_vp, _i, _i, _i] + [_vp] * 7 + [_i, _i, _i] + [_vp] * 8 + [_sz, _vp]),
-    "tsasr_lstm_bwd": (_i, [_vp] * 7 + [_i, _i, _i, _vp, _vp, _sz, _vp]),
+    "tsasr_lstm_fwd": (_i, [_vp, _i, _i, _i] + [_vp] * 7 + [_i, _i, _i] + [_vp] * 7 + [_vp]),
+    "tsasr_lstm_bwd": (_i, [_vp] * 7 + [_i, _i, _i, _vp, _vp]),
     "tsasr_onehot_dw": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
-    "tsasr_lstm_workspace_bytes": (_sz, [_i]),
-    "tsasr_lstm_fwd": (_i, [_vp, _i, _i, _i] + [_vp] * 7 + [_i, _i, _i] + [_vp] * 8 + [_sz, _vp]),
-    "tsasr_lstm_bwd": (_i, [_vp] * 7 + [_i, _i, _i, _vp, _vp, _sz, _vp]),
+    "tsasr_lstm_fwd": (_i, [_vp, _i, _i, _i] + [_vp] * 7 + [_i, _i, _i] + [_vp] * 7 + [_vp]),
+    "tsasr_lstm_bwd": (_i, [_vp] * 7 + [_i, _i, _i, _vp, _vp]),
     "tsasr_onehot_dw": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "tsasr_joint_decode_workspace_bytes": (_sz, [_i]),
     "tsasr_joint_decode_step": (_i, [_vp, _vp, _ll, _ll, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _sz, _vp]),

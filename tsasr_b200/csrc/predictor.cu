@@ -13,7 +13,7 @@
 //                          rows of W_hh live in registers, 64 per thread); a step is 16 x Hd dot products per batch tile on the
 //                          CUDA cores in fp32 (the reference's arithmetic: no bf16 anywhere, the state feeds back 100 times),
 //                          a 31-shuffle butterfly, the cell update, and one grid-wide hand-off of h_t through global memory
-//                          (per-step arrival counters, release/acquire).  x_t W_ih^T is a COLUMN GATHER of W_ih by token id --
+//                          (carried by the data itself: sentinel-filled buffer, polled with cp.async, see below).  x_t W_ih^T is a COLUMN GATHER of W_ih by token id --
 //                          no one-hot tensor, no GEMM -- prefetched a step ahead.  The relative -> absolute length conversion
 //                          (fp32 product, truncation: what torch's pack_padded_sequence does with the float lengths it is
 //                          given) happens on the device: no host synchronisation.
@@ -31,44 +31,65 @@
 
 namespace tsasr {
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+// ------------------------------------------------------------------------------------------------------------------
+// Grid-wide hand-off of one recurrence step, carried BY THE DATA.  The exchange buffer (h_t in the forward, the gate
+// gradients in the backward) is pre-filled with a sentinel bit pattern (0xFFFFFFFF: a NaN no arithmetic produces) by a
+// cudaMemsetAsync in front of the launch; every element is written exactly once, by the thread that owns it, at its
+// step.  A consumer copies the 16-utterance tile of the previous step into shared memory with cp.async (.cg: L2 only)
+// and re-fetches the 16-byte pieces that still show the sentinel until none does.  There is no flag, no fence and no
+// atomic on the critical path of a step: producer store -> L2 -> consumer copy.  Measured for 100 steps of the forward
+// (B = 16, Hd = 512): arrival counter + __threadfence 420 us, one flag per CTA polled by a warp 643 us, this scheme see
+// profiles/r2_predictor.txt.  All CTAs are co-resident (cooperative launch), so the polling cannot deadlock, and a step
+// can run at most one step ahead of the slowest CTA, so no buffer is reused.  Fail-stop after kMbarTimeoutNs like mbar_wait.
+// ------------------------------------------------------------------------------------------------------------------
+static constexpr unsigned int kSentinelBits = 0xFFFFFFFFu;
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
-
-// Grid-wide hand-off of one recurrence step: one arrival counter per step (zeroed by the host call); a CTA publishes its
-// slice with a release pattern (fence, CTA barrier, one atomic add), thread 0 of every CTA polls the counter with acquire
-// loads.  All CTAs are co-resident (cooperative launch), so polling cannot deadlock.  Measured against one flag per CTA
-// polled by a whole warp (no atomics): the single counter is faster (420 vs 643 us for 100 steps) -- same-address atomics
-// retire at about one per L2 clock, 128 acquire loads per poll do not.  Fail-stop after kMbarTimeoutNs like mbar_wait.
-__device__ __forceinline__ void grid_step_wait(const unsigned int* counter, unsigned int expected, uint32_t tag) {
-    if (threadIdx.x == 0) {
-        uint32_t spins = 0;
-        unsigned long long t0 = 0;
-        while (ld_acquire_u32(counter) < expected) {
-#if !defined(TSASR_NO_WATCHDOG)
-            if ((++spins & 1023u) == 0u) {
-                const unsigned long long now = globaltimer_ns();
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > kMbarTimeoutNs) {
-                    g_tsasr_hang_info[0] = 0xDEAD0000u | tag;
-                    g_tsasr_hang_info[1] = blockIdx.x;
-                    g_tsasr_hang_info[2] = expected;
-                    g_tsasr_hang_info[3] = ld_acquire_u32(counter);
-                    __threadfence_system();
-                    __trap();
-                }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ bool has_sentinel(const float4& v) {
+    return (__float_as_uint(v.x) == kSentinelBits) | (__float_as_uint(v.y) == kSentinelBits) | (__float_as_uint(v.z) == kSentinelBits) |
+           (__float_as_uint(v.w) == kSentinelBits);
+}
+// tile row bb (0..15) = utterance b0 + bb: ROW_F4 float4 at gbase + (b0 + bb) * row_stride (floats); rows past B are zeros
+template <int ROW_F4>
+__device__ __forceinline__ void fetch_tile_polling(float* smem_dst, const float* gbase, size_t row_stride, int b0, int B, uint32_t tag) {
+    constexpr int kTotal = kLstmBatchTile * ROW_F4;
+    for (int i = threadIdx.x; i < kTotal; i += kLstmThreads) {
+        const int bb = i / ROW_F4, k4 = i - bb * ROW_F4;
+        if (b0 + bb < B) cp_async_16(smem_dst + 4 * i, gbase + (size_t)(b0 + bb) * row_stride + 4 * k4);
+        else reinterpret_cast<float4*>(smem_dst)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_wait_all();
+    uint32_t spins = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+        bool pending = false;
+        for (int i = threadIdx.x; i < kTotal; i += kLstmThreads) {
+            const int bb = i / ROW_F4, k4 = i - bb * ROW_F4;
+            if (b0 + bb < B && has_sentinel(reinterpret_cast<const float4*>(smem_dst)[i])) {
+                cp_async_16(smem_dst + 4 * i, gbase + (size_t)(b0 + bb) * row_stride + 4 * k4);
+                pending = true;
             }
-#endif
         }
+        if (!pending) break;
+        cp_async_wait_all();
+#if !defined(TSASR_NO_WATCHDOG)
+        if ((++spins & 1023u) == 0u) {
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kMbarTimeoutNs) {
+                g_tsasr_hang_info[0] = 0xDEAD0000u | tag;
+                g_tsasr_hang_info[1] = blockIdx.x;
+                g_tsasr_hang_info[2] = threadIdx.x;
+                g_tsasr_hang_info[3] = (unsigned)b0;
+                __threadfence_system();
+                __trap();
+            }
+        }
+#endif
     }
     __syncthreads();
-}
-__device__ __forceinline__ void grid_step_publish(unsigned int* counter) {
-    __threadfence();   // this thread's global writes of the step are visible device-wide ...
-    __syncthreads();   // ... for every thread of the CTA, before one of them signals
-    if (threadIdx.x == 0) atomicAdd(counter, 1u);
 }
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
@@ -164,7 +185,6 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_fwd_kernel(const Lst
                 }
             }
         }
-        if (u > 0) grid_step_wait(p.sync + (u - 1), gridDim.x, 0xA00);
 #pragma unroll
         for (int ps = 0; ps < kLstmMaxPasses; ++ps) {
             if (ps >= passes) break;
@@ -172,15 +192,8 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_fwd_kernel(const Lst
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
             if (u > 0) {
-                // h_{u-1} of this batch tile: out[b, u-1, :] (L2 only: other SMs wrote it a moment ago)
-                for (int i = threadIdx.x; i < kLstmBatchTile * (Hd / 4); i += kLstmThreads) {
-                    const int bb = i / (Hd / 4), k4 = i - bb * (Hd / 4);
-                    const int b = ps * kLstmBatchTile + bb;
-                    float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (b < B) hv = __ldcg(reinterpret_cast<const float4*>(p.out + ((size_t)b * U + (u - 1)) * Hd) + k4);
-                    reinterpret_cast<float4*>(h_s)[i] = hv;
-                }
-                __syncthreads();
+                // h_{u-1} of this batch tile: out[b, u-1, :], as soon as its owners have written it
+                fetch_tile_polling<Hd / 4>(h_s, p.out + (size_t)(u - 1) * Hd, (size_t)U * Hd, ps * kLstmBatchTile, B, 0xA00);
 #pragma unroll
                 for (int q = 0; q < KPL / 4; ++q) {
 #pragma unroll
@@ -232,9 +245,8 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_fwd_kernel(const Lst
                     if (p.c_n) p.c_n[(size_t)b * Hd + j] = c_state[ps];
                 }
             }
-            if (ps + 1 < passes) __syncthreads();  // h_s is overwritten by the next batch tile
+            __syncthreads();  // h_s is overwritten by the next batch tile / the next step
         }
-        if (u + 1 < U) grid_step_publish(p.sync + u);
     }
 }
 
@@ -286,19 +298,12 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_bwd_kernel(const Lst
                 }
             }
         }
-        if (u < U - 1) grid_step_wait(p.sync + (u + 1), gridDim.x, 0xB00);
 #pragma unroll
         for (int ps = 0; ps < kLstmMaxPasses; ++ps) {
             if (ps >= passes) break;
             if (u < U - 1) {
-                for (int i = threadIdx.x; i < kLstmBatchTile * (G / 4); i += kLstmThreads) {
-                    const int bb = i / (G / 4), k4 = i - bb * (G / 4);
-                    const int b = ps * kLstmBatchTile + bb;
-                    float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (b < B) v4 = __ldcg(reinterpret_cast<const float4*>(p.dG + ((size_t)b * U + (u + 1)) * G) + k4);
-                    reinterpret_cast<float4*>(dg_s)[i] = v4;
-                }
-                __syncthreads();
+                // gate gradients of step u+1 of this batch tile, as soon as their owners have written them
+                fetch_tile_polling<G / 4>(dg_s, p.dG + (size_t)(u + 1) * G, (size_t)U * G, ps * kLstmBatchTile, B, 0xB00);
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -344,9 +349,8 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_bwd_kernel(const Lst
                     dc_next[ps] = 0.f;
                 }
             }
-            if (ps + 1 < passes) __syncthreads();  // dg_s / red are overwritten by the next batch tile
+            __syncthreads();  // dg_s / red are overwritten by the next batch tile / the next step
         }
-        if (u > 0) grid_step_publish(p.sync + u);
     }
 }
 

@@ -23,14 +23,13 @@ struct LstmFwdParams {
     const float* rel_lengths;   // [B] relative lengths (SpeechBrain), or nullptr ...
     const int* abs_lengths;     // ... absolute ones
     int B, U, Hd;
-    float* out;                 // [B,U,Hd] h_t, zeros at padded positions; also the grid-wide hand-off buffer
+    float* out;                 // [B,U,Hd] h_t, zeros at padded positions; also the grid-wide hand-off buffer (sentinel-filled)
     float* hprev;               // [B,U,Hd] h_{t-1} (the X operand of dW_hh), or nullptr
     float* gates;               // [B,U,4,Hd] activated gates i,f,g,o, or nullptr
     float* cells;               // [B,U,Hd] c_t, or nullptr
     float* h_n;                 // [B,Hd] or nullptr
     float* c_n;                 // [B,Hd] or nullptr
     int* lengths_out;           // [B] absolute lengths as used, or nullptr
-    unsigned int* sync;         // [U] zero-initialised arrival counters
 };
 
 struct LstmBwdParams {
@@ -42,8 +41,7 @@ struct LstmBwdParams {
     const float* cells;
     const int* lengths;         // [B] absolute
     int B, U, Hd;
-    float* dG;                  // [B,U,4Hd] d loss / d gate pre-activations (zeros at padded positions)
-    unsigned int* sync;         // [U] zero-initialised arrival counters
+    float* dG;                  // [B,U,4Hd] d loss / d gate pre-activations (zeros at padded positions); sentinel-filled on entry
 };
 
 size_t lstm_fwd_smem_bytes(int B, int U, int Hd, bool onehot);

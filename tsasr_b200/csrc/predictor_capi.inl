@@ -11,26 +11,20 @@ static int check_lstm_dims(int B, int U, int Hd) {
     return TSASR_OK;
 }
 
-static int lstm_sync(void* workspace, size_t workspace_bytes, int U, cudaStream_t st, unsigned int** out) {
-    const size_t need = tsasr_lstm_workspace_bytes(U);
-    REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
-    if (workspace_bytes < need) return fail(TSASR_E_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
-    cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);  // the per-step arrival counters start at zero
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync (lstm counters)");
-    *out = static_cast<unsigned int*>(workspace);
-    return TSASR_OK;
+// the hand-off buffer of a recurrent kernel starts as all-sentinel (0xFFFFFFFF), see predictor.cu
+static int fill_sentinel(void* buf, size_t bytes, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(buf, 0xFF, bytes, st);
+    return e == cudaSuccess ? TSASR_OK : cuda_fail(e, "cudaMemsetAsync (lstm hand-off buffer)");
 }
 
 }  // namespace
 
 extern "C" {
 
-size_t tsasr_lstm_workspace_bytes(int U) { return U >= 1 ? ((size_t)U * sizeof(unsigned int) + 255) / 256 * 256 : 0; }
-
 int tsasr_lstm_fwd(const void* tokens, int tokens_i64, int blank, int n_embed, const float* xw, const float* W_ih, const float* W_hh,
                    const float* b_ih, const float* b_hh, const float* rel_lengths, const int32_t* abs_lengths, int B, int U, int Hd,
                    float* out, float* hprev, float* gates, float* cells, float* h_n, float* c_n, int32_t* lengths_out,
-                   void* workspace, size_t workspace_bytes, tsasr_stream_t stream) {
+                   tsasr_stream_t stream) {
     NvtxRange nvtx_range("tsasr_lstm_fwd");
     if (int rc = check_lstm_dims(B, U, Hd)) return rc;
     REQUIRE(W_hh && out && (rel_lengths || abs_lengths), "null pointer argument");
@@ -44,7 +38,7 @@ int tsasr_lstm_fwd(const void* tokens, int tokens_i64, int blank, int n_embed, c
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     LstmFwdParams p;
     memset(&p, 0, sizeof(p));
-    if (int rc = lstm_sync(workspace, workspace_bytes, U, st, &p.sync)) return rc;
+    if (int rc = fill_sentinel(out, (size_t)B * U * Hd * sizeof(float), st)) return rc;
     p.tok64 = tokens && tokens_i64 ? static_cast<const long long*>(tokens) : nullptr;
     p.tok32 = tokens && !tokens_i64 ? static_cast<const int*>(tokens) : nullptr;
     p.blank = blank; p.n_embed = n_embed;
@@ -59,8 +53,7 @@ int tsasr_lstm_fwd(const void* tokens, int tokens_i64, int blank, int n_embed, c
 }
 
 int tsasr_lstm_bwd(const float* d_out, const float* d_hn, const float* d_cn, const float* W_hh, const float* gates, const float* cells,
-                   const int32_t* lengths, int B, int U, int Hd, float* dG, void* workspace, size_t workspace_bytes,
-                   tsasr_stream_t stream) {
+                   const int32_t* lengths, int B, int U, int Hd, float* dG, tsasr_stream_t stream) {
     NvtxRange nvtx_range("tsasr_lstm_bwd");
     if (int rc = check_lstm_dims(B, U, Hd)) return rc;
     REQUIRE(d_out && W_hh && gates && cells && lengths && dG, "null pointer argument");
@@ -70,7 +63,7 @@ int tsasr_lstm_bwd(const float* d_out, const float* d_hn, const float* d_cn, con
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     LstmBwdParams p;
     memset(&p, 0, sizeof(p));
-    if (int rc = lstm_sync(workspace, workspace_bytes, U, st, &p.sync)) return rc;
+    if (int rc = fill_sentinel(dG, (size_t)B * U * 4 * Hd * sizeof(float), st)) return rc;
     p.d_out = d_out; p.d_hn = d_hn; p.d_cn = d_cn; p.W_hh = W_hh; p.gates = gates; p.cells = cells; p.lengths = lengths;
     p.B = B; p.U = U; p.Hd = Hd; p.dG = dG;
     ScopedTiming tm("lstm_seq_bwd_kernel", st);

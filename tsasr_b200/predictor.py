@@ -141,7 +141,6 @@ class LstmFunction(torch.autograd.Function):
         h_n = torch.empty((B, Hd), dtype=torch.float32, device=dev)
         c_n = torch.empty((B, Hd), dtype=torch.float32, device=dev)
         L = torch.empty((B,), dtype=torch.int32, device=dev)
-        ws = _ws(dev, lib.tsasr_lstm_workspace_bytes(U))
         x2d = xw = None
         with torch.cuda.device(dev):
             if not onehot:  # dense input: x W_ih^T + b_ih through the projection GEMM, then the recurrence
@@ -153,8 +152,7 @@ class LstmFunction(torch.autograd.Function):
             _lib.check(lib.tsasr_lstm_fwd(
                 _ptr(tokens), 1 if onehot and tokens.dtype == torch.int64 else 0, int(blank), W_ih.shape[1], _ptr(xw), W_ih.data_ptr(),
                 W_hh.data_ptr(), _ptr(b_ih), _ptr(b_hh), lengths.data_ptr() if relative else None, None if relative else lengths.data_ptr(),
-                B, U, Hd, out.data_ptr(), _ptr(hprev), _ptr(gates), _ptr(cells), h_n.data_ptr(), c_n.data_ptr(), L.data_ptr(),
-                ws.data_ptr(), ws.numel(), stream))
+                B, U, Hd, out.data_ptr(), _ptr(hprev), _ptr(gates), _ptr(cells), h_n.data_ptr(), c_n.data_ptr(), L.data_ptr(), stream))
         if need_grad:
             ctx.save_for_backward(x2d, W_ih, W_hh, tokens, hprev, gates, cells, L)
             ctx.cfg = (onehot, int(blank), b_ih is not None, b_hh is not None, tuple(x.shape) if x is not None else None)
@@ -182,9 +180,8 @@ class LstmFunction(torch.autograd.Function):
         dW_ih = torch.empty_like(W_ih) if ctx.needs_input_grad[1] else None
         dx = None
         with torch.cuda.device(dev):
-            ws = _ws(dev, lib.tsasr_lstm_workspace_bytes(U))
             _lib.check(lib.tsasr_lstm_bwd(d_out.data_ptr(), _ptr(d_hn), _ptr(d_cn), W_hh.data_ptr(), gates.data_ptr(), cells.data_ptr(),
-                                          L.data_ptr(), B, U, Hd, dG.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+                                          L.data_ptr(), B, U, Hd, dG.data_ptr(), stream))
             # dW_hh = dG^T h_prev, db_ih = db_hh = column sums of dG: one split-K GEMM with the row of ones
             ws2 = _ws(dev, lib.tsasr_linear_bwd_workspace_bytes(B * U, Hd, G))
             _lib.check(lib.tsasr_linear_bwd(dG.data_ptr(), hprev.data_ptr(), None, B * U, Hd, G, None, dW_hh.data_ptr(), db.data_ptr(),
