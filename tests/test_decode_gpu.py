@@ -160,3 +160,59 @@ def test_cuda_graph_greedy_matches_the_plain_on_device_loop(golden):
     got_h, got_s, _, _ = decode.greedy_decode_cuda_graph(tn2, pred.layers(), step, blank_id=0)
     assert got_h == want_h
     np.testing.assert_allclose(float(got_s), float(want_s), rtol=1e-5)
+
+
+# ---- beam search: all utterances searched concurrently (tsasr_b200.decode.beam_search_batched) ----
+def _beam_golden(g, gb, device):
+    pred, head, tjoint, tn, _ = _golden_modules(g, device)
+    with torch.no_grad():
+        head.weight.copy_(torch.tensor(gb["W"]).to(device))
+        head.bias.copy_(torch.tensor(gb["b"]).to(device))
+    beam_size, nbest = (int(x) for x in gb["cfg"])
+    state_beam, expand_beam = (float(x) for x in gb["beams"])
+    B = tn.shape[0]
+    hyps, o = [], 0
+    for n in gb["hyp_lens"]:
+        hyps.append([int(x) for x in gb["hyp_flat"][o:o + int(n)]])
+        o += int(n)
+    nbest_ref, scores_ref, o = [], [], 0
+    for n in gb["hyp_counts"]:
+        nbest_ref.append(hyps[o:o + int(n)])
+        scores_ref.append([float(x) for x in gb["scores"][o:o + int(n)]])
+        o += int(n)
+    assert len(nbest_ref) == B
+    return pred, head, tjoint, tn, dict(beam_size=beam_size, nbest=nbest, state_beam=state_beam, expand_beam=expand_beam), nbest_ref, scores_ref
+
+
+def test_batched_beam_search_reproduces_reference_searcher_cpu(golden):
+    """CPU (no kernels involved): the concurrent search -- one coroutine per utterance, one batched network evaluation
+    per round -- gives exactly the n-best lists and scores of the reference's sequential searcher class
+    (tests/golden/beam_decode.npz, made by oracle/make_golden_beam.py with the REAL TransducerBeamSearcher)."""
+    g, gb = golden("greedy_decode"), golden("beam_decode")
+    pred, head, tjoint, tn, cfg, nbest_ref, scores_ref = _beam_golden(g, gb, "cpu")
+    step = eager_joint_step(tjoint, [head], torch.nn.LogSoftmax(dim=-1))
+    best, score, nbest, nbest_scores = decode.beam_search_batched(tn, pred.layers(), step, blank_id=0, **cfg)
+    assert nbest == nbest_ref and best == [n[0] for n in nbest_ref]
+    for got, want in zip(nbest_scores, scores_ref):
+        np.testing.assert_allclose(np.array(got, dtype=np.float64), want, rtol=1e-5)
+    np.testing.assert_allclose(float(score), float(gb["mean_exp_score"]), rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_batched_beam_search_with_fused_step_vs_reference_golden(golden):
+    """The same on the GPU with the fused joint step, through ``patch_searcher`` (beam_size > 1): n-best label sequences
+    bit-exact against the reference's searcher, one device->host copy per expansion round."""
+    g, gb = golden("greedy_decode"), golden("beam_decode")
+    d = torch.device("cuda:0")
+    pred, head, tjoint, tn, cfg, nbest_ref, scores_ref = _beam_golden(g, gb, d)
+    torch.backends.cudnn.allow_tf32 = False
+    searcher = types.SimpleNamespace(tjoint=tjoint, classifier_network=[head], softmax=torch.nn.LogSoftmax(dim=-1),
+                                     decode_network_lst=pred.layers(), blank_id=0, lm_weight=0.0, **cfg)
+    assert decode.patch_searcher(searcher, on_device_greedy=True)
+    launches0 = tsasr_b200._lib.launch_count()
+    best, score, nbest, nbest_scores = searcher.searcher(tn)
+    assert tsasr_b200._lib.launch_count() > launches0  # the fused joint step ran
+    assert nbest == nbest_ref
+    for got, want in zip(nbest_scores, scores_ref):
+        np.testing.assert_allclose(np.array(got, dtype=np.float64), want, rtol=1e-4)
+    np.testing.assert_allclose(float(score), float(gb["mean_exp_score"]), rtol=1e-4)

@@ -233,11 +233,122 @@ def greedy_decode_cuda_graph(tn_output, decode_network_lst, joint_step, blank_id
     return hyps, score, None, None
 
 
+def _hyp_key(h):
+    """``get_transducer_key`` (SB/decoders/transducer.py:527-542): length-normalised log-score."""
+    return h["logp_score"] / len(h["prediction"])
+
+
+def _beam_search_one(n_frames, beam_size, nbest, state_beam, expand_beam, blank_id):
+    """The reference's per-utterance beam search (SB/decoders/transducer.py:245-352, no LM) as a GENERATOR: wherever the
+    reference evaluates the prediction network + joint for ``a_best_hyp`` (:296-309) the generator yields
+    ``(frame, last token, hidden state)`` and is sent back ``(top-k log-probs, top-k positions, new hidden)``.
+    Scores are float32 scalars added in float32, as the reference's 0-dim CUDA tensors are, so every comparison
+    (arg-max over hypotheses, state_beam / expand_beam pruning, the final sort) sees the reference's numbers.
+    Returns (n-best label lists, their length-normalised scores)."""
+    beam_hyps = [{"prediction": [blank_id], "logp_score": 0.0, "hidden_dec": None}]
+    for t_step in range(n_frames):
+        process_hyps, beam_hyps = beam_hyps, []                                       # :274-276
+        while True:
+            if len(beam_hyps) >= beam_size:                                           # :278-279
+                break
+            a_best = max(process_hyps, key=_hyp_key)                                  # :281-283
+            if len(beam_hyps) > 0:                                                    # :286-293
+                b_best = max(beam_hyps, key=_hyp_key)
+                if b_best["logp_score"] >= state_beam + a_best["logp_score"]:
+                    break
+            for i, h in enumerate(process_hyps):                                      # :296 (remove THIS hypothesis)
+                if h is a_best:
+                    del process_hyps[i]
+                    break
+            logp_targets, positions, hidden = yield t_step, a_best["prediction"][-1], a_best["hidden_dec"]
+            best_logp = logp_targets[0] if positions[0] != blank_id else logp_targets[1]  # :320-324
+            for j in range(len(logp_targets)):                                        # :327-351
+                topk_hyp = {"prediction": a_best["prediction"][:], "logp_score": a_best["logp_score"] + logp_targets[j],
+                            "hidden_dec": a_best["hidden_dec"]}
+                if positions[j] == blank_id:
+                    beam_hyps.append(topk_hyp)
+                    continue
+                if logp_targets[j] >= best_logp - expand_beam:
+                    topk_hyp["prediction"].append(int(positions[j]))
+                    topk_hyp["hidden_dec"] = hidden
+                    process_hyps.append(topk_hyp)
+    best = sorted(beam_hyps, key=_hyp_key, reverse=True)[:nbest]                      # :353-360
+    return [h["prediction"][1:] for h in best], [h["logp_score"] / len(h["prediction"]) for h in best]
+
+
+def _stack_hidden(hiddens, template):
+    """Per-row hidden states (each a tensor [layers,1,H], a tuple of such, or None = initial state) -> one batched state
+    with the structure of ``template`` (the state a batched call returned); None when every row is at its initial state
+    and no template exists yet."""
+    if template is None:
+        return None  # first evaluation of every utterance: all rows start from the initial state
+    def zeros_like_row(t):
+        return torch.zeros_like(t[:, :1])
+    if isinstance(template, tuple):
+        return tuple(torch.cat([(h[k] if h is not None else zeros_like_row(template[k])) for h in hiddens], dim=1)
+                     for k in range(len(template)))
+    return torch.cat([(h if h is not None else zeros_like_row(template)) for h in hiddens], dim=1)
+
+
+def _row_hidden(hidden, r):
+    if hidden is None:
+        return None
+    if isinstance(hidden, tuple):
+        return tuple(h[:, r:r + 1] for h in hidden)
+    return hidden[:, r:r + 1]
+
+
+def beam_search_batched(tn_output, decode_network_lst, joint_step, blank_id=0, beam_size=4, nbest=5, state_beam=2.3,
+                        expand_beam=2.3):
+    """``TransducerBeamSearcher.transducer_beam_search_decode`` (SB/decoders/transducer.py:220-373, ``lm_weight == 0``)
+    with the B utterances searched CONCURRENTLY: the reference decodes them one after the other and evaluates the
+    prediction network and the joint for ONE hypothesis at a time (batch 1, ~15 launches and five ``.item()`` / tensor
+    comparisons that synchronise the stream per expansion); here every utterance's search is a coroutine, one round
+    evaluates the pending hypothesis of every utterance in one batched prediction-network step and one batched joint
+    step, and ONE device->host copy per round brings the top-k back.  Rounds = the longest utterance's expansions
+    instead of the sum over utterances.  The searches themselves are the reference's, decision for decision (rows of a
+    batched step are independent).  Returns the reference's 4-tuple."""
+    B, T = tn_output.shape[0], tn_output.shape[1]
+    dev = tn_output.device
+    searches = [_beam_search_one(T, beam_size, nbest, state_beam, expand_beam, blank_id) for _ in range(B)]
+    pending, results = {}, [None] * B
+    for i, g in enumerate(searches):
+        try:
+            pending[i] = next(g)
+        except StopIteration as stop:  # T == 0
+            results[i] = stop.value
+    template = None
+    with torch.no_grad():
+        while pending:
+            idx = sorted(pending)
+            frames = torch.tensor([pending[i][0] for i in idx], device=dev)
+            tokens = torch.tensor([[pending[i][1]] for i in idx], device=dev, dtype=torch.int32)
+            hidden_in = _stack_hidden([pending[i][2] for i in idx], template)
+            out_pn, hidden = _forward_pn(tokens, decode_network_lst, hidden_in)        # :297-303, all utterances at once
+            if template is None:
+                template = hidden
+            h_t = tn_output[torch.tensor(idx, device=dev), frames]                     # [n, H]
+            log_probs = joint_step(h_t.unsqueeze(1).unsqueeze(1), out_pn.unsqueeze(1))  # :304-309
+            logp, pos = torch.topk(log_probs.reshape(len(idx), -1), k=beam_size, dim=-1)  # :317-319
+            logp_h, pos_h = logp.to(torch.float32).cpu().numpy(), pos.cpu().numpy()    # the round's only device->host copy
+            for r, i in enumerate(idx):
+                try:
+                    pending[i] = searches[i].send((logp_h[r], pos_h[r], _row_hidden(hidden, r)))
+                except StopIteration as stop:
+                    results[i] = stop.value
+                    del pending[i]
+    nbest_batch = [r[0] for r in results]
+    nbest_batch_score = [r[1] for r in results]
+    score = torch.Tensor([float(s[0]) for s in nbest_batch_score]).exp().mean()
+    return [n[0] for n in nbest_batch], score, nbest_batch, nbest_batch_score
+
+
 def patch_searcher(searcher, on_device_greedy=False):
     """Replace ``searcher._joint_forward_step`` by the fused step (returns True when patched).
     ``on_device_greedy``: additionally replace the greedy searcher (``beam_size <= 1``) by ``greedy_decode_on_device``
     -- same hypotheses and score, no per-frame host synchronisation; ``"graph"`` selects the CUDA-graph variant (one
-    graph launch per frame)."""
+    graph launch per frame) -- and the beam searcher (``beam_size > 1``, no LM) by ``beam_search_batched`` (all utterances
+    searched concurrently, one batched network evaluation and one device->host copy per expansion round)."""
     step = fused_joint_forward_step(searcher.tjoint, searcher.classifier_network, searcher.softmax)
     if step is None:
         return False
@@ -250,4 +361,12 @@ def patch_searcher(searcher, on_device_greedy=False):
 
         searcher.transducer_greedy_decode = types.MethodType(greedy, searcher)
         searcher.searcher = searcher.transducer_greedy_decode
+    elif on_device_greedy and getattr(searcher, "lm_weight", 0.0) <= 0:
+
+        def beam(self, tn_output):
+            return beam_search_batched(tn_output, self.decode_network_lst, self._joint_forward_step, self.blank_id, self.beam_size,
+                                       getattr(self, "nbest", 1), getattr(self, "state_beam", 2.3), getattr(self, "expand_beam", 2.3))
+
+        searcher.transducer_beam_search_decode = types.MethodType(beam, searcher)
+        searcher.searcher = searcher.transducer_beam_search_decode
     return True
