@@ -332,6 +332,73 @@ def reference_gpu_leg(cfg, dev):
     return out
 
 
+def next_rows_leg(cfg, dev):
+    """SURVEY.md section 8f rows N1 and N3 on this box, beside the reference's own ops at the workload's shape: the two
+    projections (tsasr_b200.Linear vs torch fp32 nn.Linear = what speechbrain's Linear runs) and the prediction network
+    (tsasr_b200.Embedding + LSTM vs one-hot embedding -> pack_padded_sequence with its .cpu() -> cuDNN LSTM), forward +
+    backward through autograd, CUDA events, 3 warm-ups, median of 10.  Not part of `value` / `e2e` (BASELINE's metric is the
+    joint + loss path); reported so that the rows either side of the path have driver-visible numbers."""
+    import tsasr_b200
+
+    B, T, U, V, H = (cfg[k] for k in "BTUVH")
+    out = {"what": "forward + backward, us, ours vs the reference's ops on the same box (CUDA events, median of 10)"}
+
+    def med(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(10):
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            fn()
+            e_.record()
+            torch.cuda.synchronize(dev)
+            ts.append(s_.elapsed_time(e_) * 1e3)
+        return statistics.median(ts)
+
+    try:
+        torch.manual_seed(0)
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        for name, R, K in (("encoder_proj", B * T, 256), ("decoder_proj", B * U, 512)):   # yaml:172-174,187-189
+            ours, ref = tsasr_b200.Linear(H, input_size=K).to(dev), torch.nn.Linear(K, H).to(dev)
+            x = torch.randn(R, K, device=dev, requires_grad=True)
+            gy = torch.randn(R, H, device=dev)
+            out[name] = {"shape": [R, K, H], "ours_us": med(lambda: ours(x).backward(gy)), "reference_ops_us": med(lambda: ref(x).backward(gy))}
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        Hd = 512                                                                         # yaml:176-185
+        emb = tsasr_b200.Embedding(num_embeddings=V, consider_as_one_hot=True, blank_id=0).to(dev)
+        ours = tsasr_b200.LSTM(input_shape=[None, None, V - 1], hidden_size=Hd).to(dev)
+        ref = torch.nn.LSTM(V - 1, Hd, batch_first=True).to(dev)
+        ref.load_state_dict({k[4:]: v for k, v in ours.state_dict().items()})
+        tokens = torch.randint(1, V, (B, U), device=dev)
+        tokens[:, 0] = 0
+        rel = torch.rand(B, device=dev) * 0.6 + 0.4
+        rel[0] = 1.0
+        gy = torch.randn(B, U, Hd, device=dev)
+
+        def ours_step():
+            ours(emb(tokens), lengths=rel)[0].backward(gy)
+
+        def ref_step():
+            x = torch.nn.functional.embedding(tokens, emb.Embedding.weight, padding_idx=0)          # SB/nnet/embedding.py:114
+            packed = torch.nn.utils.rnn.pack_padded_sequence(x, (rel * U).cpu(), batch_first=True, enforce_sorted=False)  # RNN.py:35
+            torch.nn.utils.rnn.pad_packed_sequence(ref(packed)[0], batch_first=True)[0].backward(gy)
+
+        with torch.no_grad():
+            a = ours(emb(tokens), lengths=rel)[0]
+            x = torch.nn.functional.embedding(tokens, emb.Embedding.weight, padding_idx=0)
+            packed = torch.nn.utils.rnn.pack_padded_sequence(x, (rel * U).cpu(), batch_first=True, enforce_sorted=False)
+            b = torch.nn.utils.rnn.pad_packed_sequence(ref(packed)[0], batch_first=True)[0]
+        out["predictor"] = {"shape": {"B": B, "U": U, "V": V, "hidden": Hd}, "ours_us": med(ours_step), "reference_ops_us": med(ref_step),
+                            "max_abs_diff_forward": float((a - b).abs().max())}
+    except Exception as ex:  # noqa: BLE001  (report, do not fail the bench)
+        out["unavailable"] = f"{type(ex).__name__}: {str(ex)[:200]}"
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_insitu(args, rank, world):
     """--config insitu: BASELINE configs[4], the full fit_batch of the real TSASR Brain with the drop-ins beside the stock
     modules (tools/insitu_step.py).  Needs the reference install under baseline/_ref."""
@@ -637,6 +704,9 @@ def main():
         del flush
         torch.cuda.empty_cache()
         ref_gpu = reference_gpu_leg(cfg, dev)
+    next_rows = None
+    if rank == 0 and world == 1 and not args.no_reference_gpu and cfg["B"] <= 64:
+        next_rows = next_rows_leg(cfg, dev)
 
     if rank == 0:
         peak_burst, peak_sust, peak_hbm, peak_src = measured_peaks()
@@ -701,6 +771,8 @@ def main():
                 if "ms_per_step" in ref_gpu.get(k, {}):
                     ref_gpu[k]["speedup_of_e2e_over_it"] = ref_gpu[k]["ms_per_step"] / e2e_ms
             out["reference_gpu"] = ref_gpu
+        if next_rows is not None:
+            out["next_rows"] = next_rows
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, secs = cpu_reference_step(CPU_SAMPLE, threads)
