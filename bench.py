@@ -366,6 +366,11 @@ def next_rows_leg(cfg, dev):
             x = torch.randn(R, K, device=dev, requires_grad=True)
             gy = torch.randn(R, H, device=dev)
             out[name] = {"shape": [R, K, H], "ours_us": med(lambda: ours(x).backward(gy)), "reference_ops_us": med(lambda: ref(x).backward(gy))}
+            _lib.kernel_timing(True)   # GPU time of our kernels alone (the event-bracketed loop above is host-bound at this size)
+            ours(x).backward(gy)
+            torch.cuda.synchronize(dev)
+            out[name]["ours_kernels_us"] = {k: round(v[0] * 1e3, 1) for k, v in _lib.kernel_timings().items()}
+            _lib.kernel_timing(False)
         torch.backends.cuda.matmul.allow_tf32 = tf32
         Hd = 512                                                                         # yaml:176-185
         emb = tsasr_b200.Embedding(num_embeddings=V, consider_as_one_hot=True, blank_id=0).to(dev)
@@ -393,6 +398,11 @@ def next_rows_leg(cfg, dev):
             b = torch.nn.utils.rnn.pad_packed_sequence(ref(packed)[0], batch_first=True)[0]
         out["predictor"] = {"shape": {"B": B, "U": U, "V": V, "hidden": Hd}, "ours_us": med(ours_step), "reference_ops_us": med(ref_step),
                             "max_abs_diff_forward": float((a - b).abs().max())}
+        _lib.kernel_timing(True)
+        ours_step()
+        torch.cuda.synchronize(dev)
+        out["predictor"]["ours_kernels_us"] = {k: round(v[0] * 1e3, 1) for k, v in _lib.kernel_timings().items()}
+        _lib.kernel_timing(False)
     except Exception as ex:  # noqa: BLE001  (report, do not fail the bench)
         out["unavailable"] = f"{type(ex).__name__}: {str(ex)[:200]}"
     torch.cuda.empty_cache()

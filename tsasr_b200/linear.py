@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .ops import _on_device
 from .transducer_joint import JointHandle
 
 _TWINS_PER_DEVICE = 4
@@ -57,8 +58,23 @@ def forget_twins():
     _twins.clear()
 
 
-def _workspace(dev, nbytes):
-    return torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=dev)
+_ws_bytes = {}   # (R, K, N) -> tsasr_linear_bwd_workspace_bytes
+_ws_cache = {}   # (device, stream) -> split-K workspace, grown on demand (the host time of a small GEMM's backward is
+                 # mostly allocator calls and context managers otherwise)
+
+
+def _workspace(dev, R, K, N):
+    key = (R, K, N)
+    n = _ws_bytes.get(key)
+    if n is None:
+        n = _ws_bytes[key] = max(int(_lib.load().tsasr_linear_bwd_workspace_bytes(R, K, N)), 256)
+    ck = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _ws_cache.get(ck)
+    if ws is None or ws.numel() < n:
+        if len(_ws_cache) >= 8:
+            _ws_cache.clear()
+        ws = _ws_cache[ck] = torch.empty((n,), dtype=torch.uint8, device=dev)
+    return ws
 
 
 class LinearFunction(torch.autograd.Function):
@@ -72,7 +88,7 @@ class LinearFunction(torch.autograd.Function):
         lib = _lib.load()
         y = torch.empty((R, N), dtype=torch.float32, device=dev)
         y16 = torch.empty((R, N), dtype=torch.bfloat16, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             _lib.check(lib.tsasr_linear_fwd(x2d.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
                                             R, K, N, y.data_ptr(), y16.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
         ctx.save_for_backward(x2d, weight)
@@ -96,8 +112,8 @@ class LinearFunction(torch.autograd.Function):
         db = torch.empty((N,), dtype=torch.float32, device=dev) if need_db else None
         if dx is None and dw is None:
             return None, None, None
-        ws = _workspace(dev, lib.tsasr_linear_bwd_workspace_bytes(R, K, N)) if dw is not None else None
-        with torch.cuda.device(dev):
+        ws = _workspace(dev, R, K, N) if dw is not None else None
+        with _on_device(dev):
             _lib.check(lib.tsasr_linear_bwd(dy.data_ptr(), x2d.data_ptr(), weight.data_ptr(), R, K, N,
                                             dx.data_ptr() if dx is not None else None, dw.data_ptr() if dw is not None else None,
                                             db.data_ptr() if db is not None else None, ws.data_ptr() if ws is not None else None,

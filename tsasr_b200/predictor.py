@@ -26,6 +26,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .linear import _workspace as _linear_workspace
+from .ops import _on_device
 
 logger = logging.getLogger(__name__)
 
@@ -113,10 +115,6 @@ class Embedding(nn.Module):
         return self.Embedding(x.long())  # pytorch embedding layer only accept long dtype
 
 
-def _ws(dev, nbytes):
-    return torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=dev)
-
-
 def _ptr(t):
     return t.data_ptr() if t is not None else None
 
@@ -142,7 +140,7 @@ class LstmFunction(torch.autograd.Function):
         c_n = torch.empty((B, Hd), dtype=torch.float32, device=dev)
         L = torch.empty((B,), dtype=torch.int32, device=dev)
         x2d = xw = None
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             if not onehot:  # dense input: x W_ih^T + b_ih through the projection GEMM, then the recurrence
                 x2d = x.reshape(B * U, -1)
                 if not x2d.is_contiguous():
@@ -179,11 +177,11 @@ class LstmFunction(torch.autograd.Function):
         db = torch.empty((G,), dtype=torch.float32, device=dev)
         dW_ih = torch.empty_like(W_ih) if ctx.needs_input_grad[1] else None
         dx = None
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             _lib.check(lib.tsasr_lstm_bwd(d_out.data_ptr(), _ptr(d_hn), _ptr(d_cn), W_hh.data_ptr(), gates.data_ptr(), cells.data_ptr(),
                                           L.data_ptr(), B, U, Hd, dG.data_ptr(), stream))
             # dW_hh = dG^T h_prev, db_ih = db_hh = column sums of dG: one split-K GEMM with the row of ones
-            ws2 = _ws(dev, lib.tsasr_linear_bwd_workspace_bytes(B * U, Hd, G))
+            ws2 = _linear_workspace(dev, B * U, Hd, G)
             _lib.check(lib.tsasr_linear_bwd(dG.data_ptr(), hprev.data_ptr(), None, B * U, Hd, G, None, dW_hh.data_ptr(), db.data_ptr(),
                                             ws2.data_ptr(), ws2.numel(), stream))
             if onehot:
@@ -198,7 +196,7 @@ class LstmFunction(torch.autograd.Function):
                 if need_dx or dW_ih is not None:
                     if dW_ih is None:
                         dW_ih = torch.empty_like(W_ih)
-                    ws3 = _ws(dev, lib.tsasr_linear_bwd_workspace_bytes(B * U, In, G))
+                    ws3 = _linear_workspace(dev, B * U, In, G)
                     _lib.check(lib.tsasr_linear_bwd(dG.data_ptr(), x2d.data_ptr(), W_ih.data_ptr(), B * U, In, G, _ptr(dx), dW_ih.data_ptr(),
                                                     None, ws3.data_ptr(), ws3.numel(), stream))
                 if dx is not None:
