@@ -339,6 +339,7 @@ def next_rows_leg(cfg, dev):
     backward through autograd, CUDA events, 3 warm-ups, median of 10.  Not part of `value` / `e2e` (BASELINE's metric is the
     joint + loss path); reported so that the rows either side of the path have driver-visible numbers."""
     import tsasr_b200
+    from tsasr_b200 import _lib
 
     B, T, U, V, H = (cfg[k] for k in "BTUVH")
     out = {"what": "forward + backward, us, ours vs the reference's ops on the same box (CUDA events, median of 10)"}
