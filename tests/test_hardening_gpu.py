@@ -252,3 +252,85 @@ def test_deferred_finite_check_reports_one_step_late_without_syncing():
     assert chk.flush() is True and chk.deferred_steps == 3
     tsasr_b200.monitor.uninstall(b)
     assert b.check_gradients(torch.tensor(3.0, device=d)) is True and b.seen[-1] == 3.0
+
+
+def _guarded_f32(n_elems):
+    buf, view, start = _guarded(4 * n_elems)
+    return buf, view.view(torch.float32), start, 4 * n_elems
+
+
+@pytest.mark.parametrize("R,K,N", [(137, 100, 29), (129, 65, 257), (300, 64, 128), (1600, 512, 640)])
+def test_canaries_around_the_projection_kernels(R, K, N):
+    """tsasr_linear_fwd / tsasr_linear_bwd write exactly their outputs (ragged tiles, scalar and vector store paths,
+    split-K workspace): guard bands around Y, Y_bf16, dX, dW, db and the workspace stay intact."""
+    d = _dev()
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(R + N)
+    x, w, b = torch.randn(R, K, generator=g).to(d), (0.1 * torch.randn(N, K, generator=g)).to(d), torch.randn(N, generator=g).to(d)
+    dy = torch.randn(R, N, generator=g).to(d)
+    st = torch.cuda.current_stream(d).cuda_stream
+    bufs = {}
+    for name, n in (("y", R * N), ("dx", R * K), ("dw", N * K), ("db", N)):
+        bufs[name] = _guarded_f32(n)
+    y16_buf, y16_view, y16_start = _guarded(2 * R * N)
+    ws_n = int(lib.tsasr_linear_bwd_workspace_bytes(R, K, N))
+    ws_buf, ws_view, ws_start = _guarded(ws_n)
+    _lib.check(lib.tsasr_linear_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), R, K, N, bufs["y"][1].data_ptr(), y16_view.data_ptr(), st))
+    _lib.check(lib.tsasr_linear_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), R, K, N, bufs["dx"][1].data_ptr(), bufs["dw"][1].data_ptr(),
+                                    bufs["db"][1].data_ptr(), ws_view.data_ptr(), ws_n, st))
+    torch.cuda.synchronize()
+    for name, (buf, view, start, nbytes) in bufs.items():
+        assert _guards_intact(buf, start, nbytes), name
+        assert torch.isfinite(view).all(), name
+    assert _guards_intact(y16_buf, y16_start, 2 * R * N) and _guards_intact(ws_buf, ws_start, ws_n)
+    ref = torch.nn.functional.linear(x, w, b)
+    assert (bufs["y"][1].view(R, N) - ref).abs().max().item() <= 3e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("B,U,V,Hd", [(5, 7, 13, 128), (17, 9, 40, 256), (33, 5, 21, 512)])
+def test_canaries_around_the_predictor_kernels(B, U, V, Hd):
+    """tsasr_lstm_fwd / tsasr_lstm_bwd / tsasr_onehot_dw with batch sizes that leave the last batch tile partly empty:
+    every output (incl. the sentinel-filled hand-off buffers) is written exactly, nothing else is touched."""
+    d = _dev()
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(B + U)
+    G = 4 * Hd
+    tokens = torch.randint(0, V, (B, U), generator=g, dtype=torch.int32).to(d)
+    W_ih = (0.1 * torch.randn(G, V - 1, generator=g)).to(d)
+    W_hh = (0.05 * torch.randn(G, Hd, generator=g)).to(d)
+    b_ih, b_hh = (0.1 * torch.randn(G, generator=g)).to(d), (0.1 * torch.randn(G, generator=g)).to(d)
+    rel = (torch.rand(B, generator=g) * 0.8 + 0.2).to(d)
+    d_out = torch.randn(B, U, Hd, generator=g).to(d)
+    st = torch.cuda.current_stream(d).cuda_stream
+    bufs = {}
+    for name, n in (("out", B * U * Hd), ("hprev", B * U * Hd), ("gates", B * U * G), ("cells", B * U * Hd), ("h_n", B * Hd), ("c_n", B * Hd),
+                    ("dG", B * U * G), ("dW_ih", G * (V - 1))):
+        bufs[name] = _guarded_f32(n)
+    L_buf, L_view, L_start = _guarded(4 * B)
+    p = {k: v[1].data_ptr() for k, v in bufs.items()}
+    _lib.check(lib.tsasr_lstm_fwd(tokens.data_ptr(), 0, 0, V - 1, None, W_ih.data_ptr(), W_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(),
+                                  rel.data_ptr(), None, B, U, Hd, p["out"], p["hprev"], p["gates"], p["cells"], p["h_n"], p["c_n"],
+                                  L_view.data_ptr(), st))
+    _lib.check(lib.tsasr_lstm_bwd(d_out.data_ptr(), None, None, W_hh.data_ptr(), p["gates"], p["cells"], L_view.data_ptr(), B, U, Hd, p["dG"], st))
+    _lib.check(lib.tsasr_onehot_dw(tokens.data_ptr(), 0, 0, V - 1, p["dG"], B * U, G, p["dW_ih"], st))
+    torch.cuda.synchronize()
+    L = L_view.view(torch.int32).cpu()
+    assert L.tolist() == (rel.cpu() * U).to(torch.int64).tolist()
+    for name, (buf, view, start, nbytes) in bufs.items():
+        assert _guards_intact(buf, start, nbytes), name
+    assert _guards_intact(L_buf, L_start, 4 * B)
+    # no sentinel (NaN) survives in the hand-off buffers; padded positions are exact zeros
+    out, dG = bufs["out"][1].view(B, U, Hd), bufs["dG"][1].view(B, U, G)
+    assert torch.isfinite(out).all() and torch.isfinite(dG).all() and torch.isfinite(bufs["dW_ih"][1]).all()
+    for b_ in range(B):
+        assert not out[b_, int(L[b_]):].any() and not dG[b_, int(L[b_]):].any()
+    # positions whose gates were never written (padding) are never read: gates / cells there still hold the canary fill
+    ref = torch.nn.LSTM(V - 1, Hd, batch_first=True).to(d)
+    with torch.no_grad():
+        ref.weight_ih_l0.copy_(W_ih); ref.weight_hh_l0.copy_(W_hh); ref.bias_ih_l0.copy_(b_ih); ref.bias_hh_l0.copy_(b_hh)
+        onehot = torch.zeros(B, U, V - 1, device=d)
+        nz = tokens != 0
+        onehot[nz, (tokens[nz] - 1).long()] = 1.0
+        ref_out = ref(onehot)[0]
+    for b_ in range(B):
+        assert (out[b_, :int(L[b_])] - ref_out[b_, :int(L[b_])]).abs().max().item() < 2e-5 if int(L[b_]) else True

@@ -33,6 +33,7 @@ logger = logging.getLogger(__name__)
 
 FUSED_HIDDEN_SIZES = (128, 256, 512)  # check_lstm_dims (csrc/predictor_capi.inl)
 FUSED_MAX_BATCH = 64
+FUSED_MAX_POSITIONS = 40000  # B*U W_ih column indices live in shared memory beside the 32 KB state tile (lstm_fwd_smem_bytes)
 
 
 class OneHotHandle(torch.Tensor):
@@ -246,6 +247,10 @@ class LSTM(nn.Module):
             _warn_once(f"LSTM hidden size {r.hidden_size} is outside {FUSED_HIDDEN_SIZES}: using the reference's cuDNN path")
             return False
         if x.dim() != 3 or x.shape[1] < 2 or not (0 < x.shape[0] <= FUSED_MAX_BATCH):
+            return False
+        if isinstance(x, OneHotHandle) and x.shape[0] * x.shape[1] > FUSED_MAX_POSITIONS:
+            _warn_once(f"{x.shape[0]} x {x.shape[1]} token positions exceed the shared-memory table of the fused recurrence "
+                       f"({FUSED_MAX_POSITIONS}): using the reference's cuDNN path")
             return False
         w = r.weight_hh_l0
         if not (x.is_cuda and w.is_cuda and w.dtype == torch.float32) or torch.is_autocast_enabled():
