@@ -325,6 +325,7 @@ def test_canaries_around_the_predictor_kernels(B, U, V, Hd):
     for b_ in range(B):
         assert not out[b_, int(L[b_]):].any() and not dG[b_, int(L[b_]):].any()
     # positions whose gates were never written (padding) are never read: gates / cells there still hold the canary fill
+    torch.backends.cudnn.allow_tf32 = False  # the reference recurrence in fp32, like the kernels (cuDNN's default is TF32)
     ref = torch.nn.LSTM(V - 1, Hd, batch_first=True).to(d)
     with torch.no_grad():
         ref.weight_ih_l0.copy_(W_ih); ref.weight_hh_l0.copy_(W_hh); ref.bias_ih_l0.copy_(b_ih); ref.bias_hh_l0.copy_(b_hh)

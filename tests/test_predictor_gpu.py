@@ -131,6 +131,7 @@ def test_predictor_agrees_with_cudnn_and_falls_back_where_it_must():
     reference's path: an initial state (decode-time single steps) and CPU tensors."""
     d = _dev()
     torch.manual_seed(3)
+    torch.backends.cudnn.allow_tf32 = False  # cuDNN's recurrence in fp32 (its default is TF32)
     B, U, V, Hd = 8, 20, 50, 512
     emb = Embedding(num_embeddings=V, consider_as_one_hot=True, blank_id=0).to(d)
     lstm = LSTM(input_shape=[None, None, V - 1], hidden_size=Hd).to(d)

@@ -52,9 +52,42 @@ __device__ __forceinline__ bool has_sentinel(const float4& v) {
            (__float_as_uint(v.w) == kSentinelBits);
 }
 // tile row bb (0..15) = utterance b0 + bb: ROW_F4 float4 at gbase + (b0 + bb) * row_stride (floats); rows past B are zeros
+// `probe`: 16 bytes per producer CTA (its 4 units of the LAST row of the tile, written among the last of its step), polled
+// first by one thread per producer: the bulk copy then starts when the step's results are (almost certainly) all there,
+// instead of fetching a tile full of sentinels and re-fetching most of it -- in the backward a tile is 128 KB per CTA and
+// a wasted round costs more than the step's arithmetic (measured: fetch 5.5 -> see profiles/r2_predictor.txt us per step).
+// Correctness never depends on the probe: every piece is still checked for the sentinel after the copy.
+__device__ __forceinline__ float4 ld_volatile_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
 template <int ROW_F4>
-__device__ __forceinline__ void fetch_tile_polling(float* smem_dst, const float* gbase, size_t row_stride, int b0, int B, uint32_t tag) {
+__device__ __forceinline__ void fetch_tile_polling(float* smem_dst, const float* gbase, size_t row_stride, int b0, int B, uint32_t tag,
+                                                   const float* probe) {
     constexpr int kTotal = kLstmBatchTile * ROW_F4;
+    if (probe != nullptr && threadIdx.x < gridDim.x) {
+        const float* pp = probe + 4 * threadIdx.x;
+        uint32_t spins = 0;
+        unsigned long long t0 = 0;
+        while (has_sentinel(ld_volatile_f4(pp))) {
+#if !defined(TSASR_NO_WATCHDOG)
+            if ((++spins & 4095u) == 0u) {
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > kMbarTimeoutNs) {
+                    g_tsasr_hang_info[0] = 0xDEAD0000u | tag | 0x80u;
+                    g_tsasr_hang_info[1] = blockIdx.x;
+                    g_tsasr_hang_info[2] = threadIdx.x;
+                    g_tsasr_hang_info[3] = (unsigned)b0;
+                    __threadfence_system();
+                    __trap();
+                }
+            }
+#endif
+        }
+    }
+    if (probe != nullptr) __syncthreads();
     for (int i = threadIdx.x; i < kTotal; i += kLstmThreads) {
         const int bb = i / ROW_F4, k4 = i - bb * ROW_F4;
         if (b0 + bb < B) cp_async_16(smem_dst + 4 * i, gbase + (size_t)(b0 + bb) * row_stride + 4 * k4);
@@ -193,7 +226,11 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_fwd_kernel(const Lst
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
             if (u > 0) {
                 // h_{u-1} of this batch tile: out[b, u-1, :], as soon as its owners have written it
-                fetch_tile_polling<Hd / 4>(h_s, p.out + (size_t)(u - 1) * Hd, (size_t)U * Hd, ps * kLstmBatchTile, B, 0xA00);
+                const int b_probe = min(ps * kLstmBatchTile + kLstmBatchTile - 1, B - 1);  // last utterance of this tile
+                if (!(p.dbg & 2))
+                    fetch_tile_polling<Hd / 4>(h_s, p.out + (size_t)(u - 1) * Hd, (size_t)U * Hd, ps * kLstmBatchTile, B, 0xA00,
+                                               (p.dbg & 4) ? nullptr : p.out + ((size_t)b_probe * U + (u - 1)) * Hd);
+                if (!(p.dbg & 1))
 #pragma unroll
                 for (int q = 0; q < KPL / 4; ++q) {
 #pragma unroll
@@ -303,10 +340,14 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_seq_bwd_kernel(const Lst
             if (ps >= passes) break;
             if (u < U - 1) {
                 // gate gradients of step u+1 of this batch tile, as soon as their owners have written them
-                fetch_tile_polling<G / 4>(dg_s, p.dG + (size_t)(u + 1) * G, (size_t)U * G, ps * kLstmBatchTile, B, 0xB00);
+                const int b_probe = min(ps * kLstmBatchTile + kLstmBatchTile - 1, B - 1);  // last utterance of this tile
+                if (!(p.dbg & 2))
+                    fetch_tile_polling<G / 4>(dg_s, p.dG + (size_t)(u + 1) * G, (size_t)U * G, ps * kLstmBatchTile, B, 0xB00,
+                                              (p.dbg & 4) ? nullptr : p.dG + ((size_t)b_probe * U + (u + 1)) * G + 3 * Hd);
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                if (!(p.dbg & 1))
 #pragma unroll
                 for (int q = 0; q < KPL / 4; ++q) {
 #pragma unroll

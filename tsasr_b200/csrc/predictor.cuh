@@ -23,6 +23,7 @@ struct LstmFwdParams {
     const float* rel_lengths;   // [B] relative lengths (SpeechBrain), or nullptr ...
     const int* abs_lengths;     // ... absolute ones
     int B, U, Hd;
+    int dbg;                    // development ablations (TSASR_DEBUG_LSTM): 1 = skip the dot products, 2 = skip the hand-off fetch, 4 = no probe before the bulk fetch
     float* out;                 // [B,U,Hd] h_t, zeros at padded positions; also the grid-wide hand-off buffer (sentinel-filled)
     float* hprev;               // [B,U,Hd] h_{t-1} (the X operand of dW_hh), or nullptr
     float* gates;               // [B,U,4,Hd] activated gates i,f,g,o, or nullptr
@@ -41,6 +42,7 @@ struct LstmBwdParams {
     const float* cells;
     const int* lengths;         // [B] absolute
     int B, U, Hd;
+    int dbg;
     float* dG;                  // [B,U,4Hd] d loss / d gate pre-activations (zeros at padded positions); sentinel-filled on entry
 };
 

@@ -11,6 +11,11 @@ static int check_lstm_dims(int B, int U, int Hd) {
     return TSASR_OK;
 }
 
+static int lstm_debug_flags() {  // development ablations, see LstmFwdParams::dbg
+    static const int v = getenv("TSASR_DEBUG_LSTM") ? atoi(getenv("TSASR_DEBUG_LSTM")) : 0;
+    return v;
+}
+
 // the hand-off buffer of a recurrent kernel starts as all-sentinel (0xFFFFFFFF), see predictor.cu
 static int fill_sentinel(void* buf, size_t bytes, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(buf, 0xFF, bytes, st);
@@ -45,6 +50,7 @@ int tsasr_lstm_fwd(const void* tokens, int tokens_i64, int blank, int n_embed, c
     p.xw = xw; p.W_ih = W_ih; p.W_hh = W_hh; p.b_ih = b_ih; p.b_hh = b_hh;
     p.rel_lengths = rel_lengths; p.abs_lengths = abs_lengths;
     p.B = B; p.U = U; p.Hd = Hd;
+    p.dbg = lstm_debug_flags();
     p.out = out; p.hprev = hprev; p.gates = gates; p.cells = cells; p.h_n = h_n; p.c_n = c_n; p.lengths_out = lengths_out;
     ScopedTiming tm("lstm_seq_fwd_kernel", st);
     cudaError_t e = launch_lstm_fwd(p, st);
@@ -66,6 +72,7 @@ int tsasr_lstm_bwd(const float* d_out, const float* d_hn, const float* d_cn, con
     if (int rc = fill_sentinel(dG, (size_t)B * U * 4 * Hd * sizeof(float), st)) return rc;
     p.d_out = d_out; p.d_hn = d_hn; p.d_cn = d_cn; p.W_hh = W_hh; p.gates = gates; p.cells = cells; p.lengths = lengths;
     p.B = B; p.U = U; p.Hd = Hd; p.dG = dG;
+    p.dbg = lstm_debug_flags();
     ScopedTiming tm("lstm_seq_bwd_kernel", st);
     cudaError_t e = launch_lstm_bwd(p, st);
     ++g_launches;
