@@ -195,3 +195,40 @@ def test_projection_oracle_against_torch():
     np.testing.assert_allclose(dx, x.grad.numpy(), rtol=1e-12)
     np.testing.assert_allclose(dw, w.grad.numpy(), rtol=1e-12)
     np.testing.assert_allclose(db, b.grad.numpy(), rtol=1e-12)
+
+
+def test_adopt_modules_swaps_in_place_and_shares_parameters():
+    """tsasr_b200.adopt_modules on modules built from the REFERENCE's class shapes (same class names and attributes as
+    SB/nnet/linear.py, embedding.py, RNN.py): the drop-ins take over the very same parameter tensors."""
+    class Linear(torch.nn.Module):          # stand-ins with the reference's names / attributes (speechbrain is not importable on CPU CI)
+        def __init__(self):
+            super().__init__()
+            self.combine_dims = False
+            self.w = torch.nn.Linear(6, 4)
+
+    class Embedding(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.num_embeddings, self.consider_as_one_hot, self.embedding_dim, self.blank_id = 7, True, 6, 0
+            self.Embedding = torch.nn.Embedding(7, 6, padding_idx=0)
+
+    class LSTM(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.reshape = False
+            self.rnn = torch.nn.LSTM(6, 8, batch_first=True)
+
+    mods = {"encoder_proj": Linear(), "decoder_proj": Linear(), "embedding": Embedding(), "decoder": LSTM(), "joiner": torch.nn.Identity()}
+    old = dict(mods)
+    assert tsasr_b200.adopt_modules(mods) == ["encoder_proj", "decoder_proj", "embedding", "decoder"]
+    assert isinstance(mods["encoder_proj"], tsasr_b200.Linear) and mods["encoder_proj"].w is old["encoder_proj"].w
+    assert isinstance(mods["embedding"], tsasr_b200.Embedding) and mods["embedding"].Embedding is old["embedding"].Embedding
+    assert isinstance(mods["decoder"], tsasr_b200.LSTM) and mods["decoder"].rnn is old["decoder"].rnn
+    assert mods["joiner"] is old["joiner"]
+    assert [n for n, _ in mods["decoder"].named_parameters()] == [n for n, _ in old["decoder"].named_parameters()]
+    # CPU tensors: the adopted modules compute what the originals compute
+    tok = torch.tensor([[0, 3, 5]])
+    x = mods["embedding"](tok)
+    y, _ = mods["decoder"](x)
+    assert torch.equal(y, old["decoder"].rnn(old["embedding"].Embedding(tok))[0])
+    assert tsasr_b200.adopt_modules(mods) == []  # idempotent

@@ -14,6 +14,8 @@ plus the functional forms ``rnnt_loss`` (torchaudio signature) and ``fused_joint
 All arithmetic runs in libtsasr_b200.so (hand-written CUDA, C ABI in include/tsasr_b200.h); there
 is no CPU path and no PyTorch fallback for the loss.
 """
+import torch as _torch
+
 from . import _lib, linear, monitor, ops, predictor  # noqa: F401
 from .functional import fused_joint_rnnt_loss, rnnt_loss  # noqa: F401
 from .linear import Linear  # noqa: F401
@@ -39,3 +41,42 @@ def install_into_speechbrain():
         sb_tl.Transducer = Transducer
     except ImportError:  # numba missing: the reference module cannot even be imported
         pass
+
+
+def adopt_modules(modules, names=("encoder_proj", "decoder_proj", "embedding", "decoder")):
+    """Swap already-constructed SpeechBrain modules for the drop-ins IN PLACE of a ``modules`` mapping (the dict handed to
+    ``Brain(modules=...)``, or a ``torch.nn.ModuleDict``), sharing their parameter tensors: the drop-in ``Linear`` takes the
+    stock module's ``w`` (nn.Linear), ``Embedding`` its ``Embedding`` (nn.Embedding), ``LSTM`` its ``rnn`` (nn.LSTM) -- no
+    copy, so optimizer state, checkpoints and DDP buckets built afterwards see the same parameters under the same names.
+    The equivalent of editing the yaml tags of INTEGRATION.md for code that builds its modules itself; call it BEFORE the
+    Brain wraps the modules in DistributedDataParallel.  Modules of other types (or missing names) are left alone.
+    Returns the list of names that were swapped."""
+    swapped = []
+    for name in names:
+        try:
+            old = modules[name]
+        except (KeyError, IndexError, TypeError):
+            continue
+        cls = type(old).__name__
+        new = None
+        if cls == "Linear" and isinstance(getattr(old, "w", None), _torch.nn.Linear) and not isinstance(old, Linear):
+            new = Linear.__new__(Linear)
+            _torch.nn.Module.__init__(new)
+            new.combine_dims = getattr(old, "combine_dims", False)
+            new.w = old.w
+        elif cls == "Embedding" and hasattr(old, "Embedding") and hasattr(old, "consider_as_one_hot") and not isinstance(old, Embedding):
+            new = Embedding.__new__(Embedding)
+            _torch.nn.Module.__init__(new)
+            new.num_embeddings, new.consider_as_one_hot = old.num_embeddings, old.consider_as_one_hot
+            new.embedding_dim, new.blank_id = old.embedding_dim, old.blank_id
+            new.Embedding = old.Embedding
+        elif cls == "LSTM" and isinstance(getattr(old, "rnn", None), _torch.nn.LSTM) and not isinstance(old, LSTM):
+            new = LSTM.__new__(LSTM)
+            _torch.nn.Module.__init__(new)
+            new.reshape = getattr(old, "reshape", False)
+            new.rnn = old.rnn
+        if new is not None:
+            new.train(old.training)
+            modules[name] = new
+            swapped.append(name)
+    return swapped
