@@ -337,7 +337,7 @@ class FusedJointRnnt(torch.autograd.Function):
         if code == _lib.F32:
             from .linear import bf16_twin
 
-            tw_enc, tw_dec = bf16_twin(enc), bf16_twin(dec)
+            tw_enc, tw_dec = bf16_twin(enc, consume=True), bf16_twin(dec, consume=True)
         b32 = bias.detach()
         if b32.dtype != torch.float32 or not b32.is_contiguous():
             b32 = b32.to(torch.float32).contiguous()

@@ -36,20 +36,24 @@ def _remember_twin(y32, y16):
         reg.popitem(last=False)
 
 
-def bf16_twin(t):
+def bf16_twin(t, consume=False):
     """The bf16 copy written together with ``t`` by ``tsasr_linear_fwd``, if ``t`` is (a full, contiguous view of) such
-    an output and has not been modified in place since; else None."""
+    an output and has not been modified in place since; else None.  ``consume``: drop the registry entry (the fused loss
+    keeps the copy alive through its autograd node from then on, so nothing outlives the step)."""
     if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.storage_offset() == 0):
         return None
     reg = _twins.get(t.device)
     if not reg:
         return None
-    hit = reg.get(t.untyped_storage().data_ptr())
+    key = t.untyped_storage().data_ptr()
+    hit = reg.get(key)
     if hit is None:
         return None
     alias, version, y16 = hit
     if alias.numel() != t.numel() or alias._version != version:
         return None
+    if consume:
+        del reg[key]
     return y16.view(t.shape)
 
 
