@@ -246,7 +246,11 @@ class LSTM(nn.Module):
         if r.hidden_size not in FUSED_HIDDEN_SIZES:
             _warn_once(f"LSTM hidden size {r.hidden_size} is outside {FUSED_HIDDEN_SIZES}: using the reference's cuDNN path")
             return False
-        if x.dim() != 3 or x.shape[1] < 2 or not (0 < x.shape[0] <= FUSED_MAX_BATCH):
+        if x.dim() != 3 or x.shape[1] < 2 or x.shape[0] < 1:
+            return False  # single steps (decoding) and degenerate shapes: the module's own torch.nn.LSTM
+        if x.shape[0] > FUSED_MAX_BATCH:
+            _warn_once(f"{x.shape[0]} utterances exceed the {FUSED_MAX_BATCH} the fused recurrence keeps state for: using the "
+                       "reference's cuDNN path")
             return False
         if isinstance(x, OneHotHandle) and x.shape[0] * x.shape[1] > FUSED_MAX_POSITIONS:
             _warn_once(f"{x.shape[0]} x {x.shape[1]} token positions exceed the shared-memory table of the fused recurrence "
