@@ -163,3 +163,36 @@ def test_bf16_twin_feeds_the_fused_loss_bit_identically():
     # a partial view is not the whole operand
     e = enc_proj(xe)
     assert tlin.bf16_twin(e[1:]) is None
+
+
+def test_linear_fuzz_small_shapes_vs_oracle():
+    """30 random shapes (ragged tiles, K tails, scalar and vector paths, split-K and single-pass dW): forward and backward
+    against the float64 oracle."""
+    rng = np.random.default_rng(2024)
+    d = _dev()
+    lib = _lib.load()
+    st = torch.cuda.current_stream(d).cuda_stream
+    for case in range(30):
+        R, K, N = int(rng.integers(1, 400)), int(rng.integers(1, 260)), int(rng.integers(1, 300))
+        if case % 5 == 0:
+            R = int(rng.integers(1000, 5000))  # enough k-blocks for a split-K dW
+        g = torch.Generator().manual_seed(case)
+        x, w = torch.randn(R, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+        b = torch.randn(N, generator=g) if case % 2 else None
+        dy = torch.randn(R, N, generator=g)
+        y, y16 = _call_fwd(x, w, b)
+        ref = oracle.linear_fwd(x.numpy(), w.numpy(), None if b is None else b.numpy())
+        bound = REL * oracle.linear_abs_bound(x.numpy(), w.numpy(), None if b is None else b.numpy()) + 1e-30
+        assert (np.abs(y.cpu().double().numpy() - ref) <= bound).all(), (case, R, K, N)
+        assert torch.equal(y16, y.bfloat16()), (case, R, K, N)
+        xd, wd, dyd = x.to(d), w.to(d), dy.to(d)
+        ws = torch.empty((lib.tsasr_linear_bwd_workspace_bytes(R, K, N) + 256,), dtype=torch.uint8, device=d)
+        dx, dw, db = torch.empty(R, K, device=d), torch.empty(N, K, device=d), torch.empty(N, device=d)
+        _lib.check(lib.tsasr_linear_bwd(dyd.data_ptr(), xd.data_ptr(), wd.data_ptr(), R, K, N, dx.data_ptr(), dw.data_ptr(), db.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), st))
+        torch.cuda.synchronize()
+        rdx, rdw, rdb = oracle.linear_bwd(dy.numpy(), x.numpy(), w.numpy())
+        a_dy, a_x, a_w = np.abs(dy.double().numpy()), np.abs(x.double().numpy()), np.abs(w.double().numpy())
+        for name, got, want, bnd in (("dx", dx, rdx, a_dy @ a_w), ("dw", dw, rdw, a_dy.T @ a_x), ("db", db, rdb, a_dy.sum(0))):
+            lim = (REL + 6e-8 * np.sqrt(R)) * bnd + 1e-30
+            assert (np.abs(got.cpu().double().numpy() - want) <= lim).all(), (case, name, R, K, N)

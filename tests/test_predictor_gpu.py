@@ -198,3 +198,28 @@ def test_predictor_chain_into_the_fused_loss():
         ref_g = pr.grad
         err = (got["rnn." + n].cpu() - ref_g).abs().max().item() / ref_g.abs().max().item()
         assert err < 1e-2, (n, err)  # bf16 dlogits noise of the fused loss, not of the predictor kernels
+
+
+def test_predictor_fuzz_vs_oracle():
+    """16 random configurations (batch sizes that leave batch tiles partly empty, up to four passes, every hidden size, tiny
+    vocabularies, blank anywhere, utterances of one step, int32 and int64 tokens): forward and backward vs the float64 oracle."""
+    rng = np.random.default_rng(7)
+    for case in range(16):
+        B, U = int(rng.integers(1, 65)), int(rng.integers(2, 24))
+        V, Hd = int(rng.integers(2, 60)), int(rng.choice([128, 256, 512]))
+        blank = int(rng.integers(0, V))
+        g = torch.Generator().manual_seed(100 + case)
+        tokens = torch.randint(0, V, (B, U), generator=g, dtype=torch.int32 if case % 2 else torch.int64)
+        k = 1.0 / Hd ** 0.5
+        params = {"weight_ih": (torch.rand(4 * Hd, V - 1, generator=g) * 2 - 1) * k, "weight_hh": (torch.rand(4 * Hd, Hd, generator=g) * 2 - 1) * k,
+                  "bias_ih": (torch.rand(4 * Hd, generator=g) * 2 - 1) * k, "bias_hh": (torch.rand(4 * Hd, generator=g) * 2 - 1) * k}
+        rel = torch.rand(B, generator=g) * (1.0 - 1.0 / U) + 1.0 / U + 1e-4   # at least one step each
+        rel.clamp_(max=1.0)
+        rel[int(rng.integers(0, B))] = 1.0
+        d_out = torch.randn(B, U, Hd, generator=g)
+        res = _run_dropins(tokens, V, blank, params, rel, d_out)
+        ref = oracle.predictor_fwd_bwd(tokens, V, blank, params, rel, d_out)
+        for key in ("out", "h_n", "c_n"):
+            _close(res[key], ref[key], 2e-5, 2e-5, f"case {case} (B={B},U={U},V={V},Hd={Hd},blank={blank}) {key}")
+        for key in ("d_weight_ih", "d_weight_hh", "d_bias_ih", "d_bias_hh"):
+            _grad_close(res[key], ref[key], f"case {case} (B={B},U={U},V={V},Hd={Hd},blank={blank}) {key}")
