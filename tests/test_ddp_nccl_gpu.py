@@ -64,7 +64,50 @@ assert all(v < 1e-2 for k, v in errs.items() if k != "loss") and errs["loss"] < 
 gw = [torch.zeros_like(head.weight.grad) for _ in range(world)]
 dist.all_gather(gw, head.weight.grad)
 assert all(torch.equal(gw[0], x) for x in gw)
-print(f"rank {rank} ok {errs}", flush=True)
+
+# ---- the projection / prediction-network drop-ins inside their OWN DDP wrappers: SpeechBrain wraps every module that has
+# trainable parameters (SB/core.py:1469-1484): decoder (tsasr_b200.LSTM) and decoder_proj (tsasr_b200.Linear); the one-hot
+# Embedding has none and stays unwrapped.  The deferred OneHotHandle must pass through DDP's input scatter, the cooperative
+# recurrence must run, and the wrapped modules' gradients must come out as the rank average of the local gradients.
+import copy
+DDP = torch.nn.parallel.DistributedDataParallel
+Vp, Hd = 30, 128
+torch.manual_seed(1)
+emb = tsasr_b200.Embedding(num_embeddings=Vp, consider_as_one_hot=True, blank_id=0).to(dev)
+lstm = tsasr_b200.LSTM(input_shape=[None, None, Vp - 1], hidden_size=Hd).to(dev)
+proj = tsasr_b200.Linear(H, input_size=Hd).to(dev)
+lstm_local, proj_local, head_local = copy.deepcopy(lstm), copy.deepcopy(proj), copy.deepcopy(head)
+ddp_lstm, ddp_proj = DDP(lstm, device_ids=[dev]), DDP(proj, device_ids=[dev])
+tok = torch.randint(0, Vp, (B, U), generator=g)
+tok[:, 0] = 0
+bos_rel = torch.tensor([1.0, 0.5, 0.75])
+
+def chain(lstm_m, proj_m, head_m):
+    for m in (lstm_m, proj_m, head_m):
+        m.zero_grad(set_to_none=True)
+    e2 = enc.to(dev).requires_grad_()
+    x = emb(tok.to(dev))
+    assert isinstance(x, tsasr_b200.OneHotHandle)
+    dec_out, _ = lstm_m(x, lengths=bos_rel.to(dev))
+    logits2 = head_m(joiner(e2[..., None, :], proj_m(dec_out)[:, None, ...]))
+    assert isinstance(logits2, tsasr_b200.JointHandle)
+    l2 = tsasr_b200.transducer_loss(logits2, targets.to(dev), in_rel.to(dev), tg_rel.to(dev), blank_index=0)
+    l2.backward()
+    torch.cuda.synchronize()
+    return l2
+
+n0 = tsasr_b200._lib.launch_count()
+chain(ddp_lstm, ddp_proj, ddp_head)
+assert tsasr_b200._lib.launch_count() - n0 >= 10          # recurrence, projection GEMMs and the fused loss all ran
+got = [p.grad.detach().clone() for m in (lstm, proj, head) for p in m.parameters()]
+chain(lstm_local, proj_local, head_local)
+want = [p.grad.detach().clone() for m in (lstm_local, proj_local, head_local) for p in m.parameters()]
+for t in want:
+    dist.all_reduce(t)
+    t /= world
+worst = max(rel(a, b) for a, b in zip(got, want))
+assert worst < 1e-5, worst                                  # deterministic kernels: DDP's average IS the average of the local runs
+print(f"rank {rank} ok {errs} predictor/projection DDP grads vs rank average: {worst:.1e}", flush=True)
 dist.destroy_process_group()
 '''
 
