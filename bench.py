@@ -651,17 +651,20 @@ def main():
         loss.backward()
         if not keep_grads:
             head.zero_grad(set_to_none=True)
-        return loss.item()  # D2H read of the step's result
+        return loss  # still on the device: the caller reads it (D2H) after queueing the next step's input copy
 
     def e2e_loop(n):
-        """n steps; step i+1's host->device copy is issued before step i's kernels, so it overlaps them."""
+        """n steps; step i+1's host->device copy is queued (copy stream) right after step i's kernels have been queued and
+        before step i's loss is read, so both the copy and the host work of issuing it overlap step i's kernels -- what a
+        pin_memory DataLoader worker does beside the training loop.  Every step still ends with a synchronous D2H read of
+        its own loss."""
         val = None
-        nxt = h2d_async()
+        cur = h2d_async()
         for i in range(n):
-            cur = nxt
+            loss = e2e_compute(*cur)
             if i + 1 < n:
-                nxt = h2d_async()
-            val = e2e_compute(*cur)
+                cur = h2d_async()
+            val = loss.item()  # D2H read of the step's result
         return val
 
     e2e_loop(3)
@@ -680,7 +683,7 @@ def main():
     # ---- N > 1: the head gradient DDP produced must be the rank average of the local gradients ----
     ddp_check = None
     if dist is not None:
-        e2e_compute(*h2d_async(), keep_grads=True)
+        e2e_compute(*h2d_async(), keep_grads=True).item()
         g_ddp = [head.weight.grad.detach().clone(), head.bias.grad.detach().clone()]
         head.zero_grad(set_to_none=True)
         e_, d_ = enc.detach().clone().requires_grad_(), dec.detach().clone().requires_grad_()
