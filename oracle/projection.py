@@ -4,7 +4,8 @@
 last dimension (:61,74), instantiated for ``encoder_proj`` / ``decoder_proj`` at
 hparams/LibriSpeechMix/conformer-t_scratch.yaml:172-174,187-189 and called at train_librispeechmix_scratch.py:122,127;
 its backward is autograd's: dX = dY W, dW = dY^T X, db = sum over rows of dY.  Restated in float64 numpy so that the fp32
-reference result and the tcgen05 result can both be placed against the exact value.  Nothing in tsasr_b200/ imports this.
+reference result and the tcgen05 result can both be placed against the exact value.  Pinned against the reference's own
+class by tests/golden/linear_proj*.npz (oracle/make_golden_projection.py).  Nothing in tsasr_b200/ imports this.
 """
 import numpy as np
 

@@ -196,3 +196,30 @@ def test_linear_fuzz_small_shapes_vs_oracle():
         for name, got, want, bnd in (("dx", dx, rdx, a_dy @ a_w), ("dw", dw, rdw, a_dy.T @ a_x), ("db", db, rdb, a_dy.sum(0))):
             lim = (REL + 6e-8 * np.sqrt(R)) * bnd + 1e-30
             assert (np.abs(got.cpu().double().numpy() - want) <= lim).all(), (case, name, R, K, N)
+
+
+@pytest.mark.parametrize("name", ["linear_proj", "linear_proj_combine", "linear_proj_nobias"])
+def test_linear_dropin_matches_reference_golden(golden, name):
+    """tsasr_b200.Linear against outputs and gradients produced by the reference's own speechbrain.nnet.linear.Linear
+    (tests/golden/linear_proj*.npz): 3-D input, combine_dims on a 4-D input, no bias."""
+    g = golden(name)
+    d = _dev()
+    x = torch.from_numpy(g["x"]).to(d).requires_grad_()
+    has_bias = "bias" in g
+    if int(g["combine_dims"]):
+        lin = tsasr_b200.Linear(g["weight"].shape[0], input_shape=[None, None, *g["x"].shape[2:]], bias=has_bias, combine_dims=True).to(d)
+    else:
+        lin = tsasr_b200.Linear(g["weight"].shape[0], input_size=g["weight"].shape[1], bias=has_bias).to(d)
+    with torch.no_grad():
+        lin.w.weight.copy_(torch.from_numpy(g["weight"]))
+        if has_bias:
+            lin.w.bias.copy_(torch.from_numpy(g["bias"]))
+    n0 = _lib.launch_count()
+    y = lin(x)
+    assert _lib.launch_count() == n0 + 1  # the tcgen05 kernel ran
+    (y * torch.from_numpy(g["d_out"]).to(d)).sum().backward()
+    torch.cuda.synchronize()
+    for got, key in ((y, "out"), (x.grad, "d_x"), (lin.w.weight.grad, "d_weight")) + (((lin.w.bias.grad, "d_bias"),) if has_bias else ()):
+        want = g[key]
+        assert tuple(got.shape) == want.shape, key
+        assert np.abs(got.detach().cpu().numpy() - want).max() <= 5e-5 * max(np.abs(want).max(), 1.0), key

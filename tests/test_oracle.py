@@ -160,3 +160,27 @@ def test_predictor_oracle_matches_reference_modules(golden, name):
         assert res["lengths"].tolist() == [13, 7, 3, 7, 1]  # 0.6 * 13 = 7.8 is truncated (the loss would round it to 8)
     for key in ("out", "h_n", "c_n", "d_weight_ih", "d_weight_hh", "d_bias_ih", "d_bias_hh") + (("d_x",) if dense is not None else ()):
         np.testing.assert_allclose(res[key].numpy(), g[key], rtol=2e-4, atol=2e-6, err_msg=key)
+
+
+# ---- projections: the restatement against the reference's own Linear class ----
+PROJECTION_GOLDEN = ["linear_proj", "linear_proj_combine", "linear_proj_nobias"]
+
+
+@pytest.mark.parametrize("name", PROJECTION_GOLDEN)
+def test_projection_oracle_matches_reference_module(golden, name):
+    """oracle/projection.py against outputs and gradients of speechbrain.nnet.linear.Linear (oracle/make_golden_projection.py
+    ran the REAL class): last-dimension product, bias, and the combine_dims flattening of 4-D inputs."""
+    from oracle import projection
+
+    g = golden(name)
+    x = g["x"]
+    if int(g["combine_dims"]) and x.ndim == 4:
+        x = x.reshape(x.shape[0], x.shape[1], -1)      # SB/nnet/linear.py:71-72
+    bias = g["bias"] if "bias" in g else None
+    np.testing.assert_allclose(projection.linear_fwd(x, g["weight"], bias), g["out"], rtol=1e-5, atol=1e-6)
+    K = x.shape[-1]
+    dx, dw, db = projection.linear_bwd(g["d_out"].reshape(-1, g["d_out"].shape[-1]), x.reshape(-1, K), g["weight"])
+    np.testing.assert_allclose(dx.reshape(g["d_x"].shape), g["d_x"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(dw, g["d_weight"], rtol=1e-5, atol=1e-5)
+    if bias is not None:
+        np.testing.assert_allclose(db, g["d_bias"], rtol=1e-5, atol=1e-5)
