@@ -231,6 +231,14 @@ static int fill_joint_params(JointParams& p, const void* enc, const void* dec, c
     if ((int)smem_layout(p.KB, ns).total > max_smem)
         return fail(TSASR_E_UNSUPPORTED, "not enough shared memory (%d B) for H=%d", max_smem, H);
     p.num_w_stages = ns;
+    // One narrow vocabulary tile on CTA pairs: W is small enough to stay in the W area for the whole kernel (see JointParams).
+    p.w_resident = 0;
+    p.w_stage_bytes = kWStageBytes;
+    static const bool narrow_ok = getenv("TSASR_DEBUG_NO_NARROW") == nullptr;
+    if (narrow_ok && use_pair() && p.NT == 1 && (size_t)(p.n_last / 2) * 128 * p.KB <= (size_t)ns * kWStageBytes) {
+        p.w_resident = 1;
+        p.w_stage_bytes = (p.n_last / 2) * 128;  // n_last is a multiple of 32: whole 8-row swizzle atoms
+    }
     static const int dbg_skip = getenv("TSASR_DEBUG_SKIP") ? atoi(getenv("TSASR_DEBUG_SKIP")) : 0;
     p.dbg_skip = dbg_skip;
     p.enc = reinterpret_cast<const __nv_bfloat16*>(enc);
@@ -244,17 +252,18 @@ struct JointMaps { CUtensorMap w; };
 static int make_joint_maps(JointMaps* m, const JointParams& p, const void* enc, const void* dec, const void* W) {
     const int tT = 1 << p.tT_log2, tU = 128 >> p.tT_log2;
     if (use_pair()) {
-        if (int rc = make_tmap_2d_bf16(&m->w, W, (uint64_t)p.V, (uint64_t)p.H, kWStageKPair, kTileN / 2, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+        const uint32_t box_rows = p.w_resident ? (uint32_t)(p.n_last / 2) : (uint32_t)(kTileN / 2);
+        if (int rc = make_tmap_2d_bf16(&m->w, W, (uint64_t)p.V, (uint64_t)p.H, kWStageKPair, box_rows, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     } else {
         if (int rc = make_tmap_2d_bf16(&m->w, W, (uint64_t)p.V, (uint64_t)p.H, kWStageK, kTileN, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
     }
     return TSASR_OK;
 }
 
-template <int MODE, bool PAIR>
+template <int MODE, bool PAIR, int NPW>
 static int launch_joint_impl(const JointMaps& maps, const JointParams& p, int num_sms, cudaStream_t st) {
     const SmemLayout L = smem_layout(p.KB, p.num_w_stages);
-    auto kern = joint_gemm_kernel<MODE, PAIR>;
+    auto kern = joint_gemm_kernel<MODE, PAIR, NPW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(joint_gemm_kernel)");
     const int tiles = p.tile_end - p.tile_begin;
@@ -277,7 +286,7 @@ static int launch_joint_impl(const JointMaps& maps, const JointParams& p, int nu
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kNumThreads);
+    cfg.blockDim = dim3(Roles<NPW>::kThreads);
     cfg.dynamicSmemBytes = L.total;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -316,7 +325,14 @@ static int launch_joint_impl(const JointMaps& maps, const JointParams& p, int nu
 
 template <int MODE>
 static int launch_joint(const JointMaps& maps, const JointParams& p, int num_sms, cudaStream_t st) {
-    return use_pair() ? launch_joint_impl<MODE, true>(maps, p, num_sms, st) : launch_joint_impl<MODE, false>(maps, p, num_sms, st);
+    if (!use_pair()) return launch_joint_impl<MODE, false, 8>(maps, p, num_sms, st);
+    // Narrow vocabularies (one vocabulary tile of at most 128 columns per cell tile, e.g. the 29 characters of the recipe as
+    // shipped): the A operand is rebuilt for every 32..128 columns of MMA work, so the kernel is paced by its producers --
+    // sixteen producer warps and one epilogue column group instead of eight and two.  TSASR_DEBUG_NO_NARROW=1: A/B runs.
+    static const bool narrow_ok = getenv("TSASR_DEBUG_NO_NARROW") == nullptr;
+    static const bool narrow_8 = getenv("TSASR_DEBUG_NARROW_8") != nullptr;  // development: resident W with the 8-producer layout
+    if (narrow_ok && !narrow_8 && p.NT == 1 && p.n_last <= kTileN / 2) return launch_joint_impl<MODE, true, 16>(maps, p, num_sms, st);
+    return launch_joint_impl<MODE, true, 8>(maps, p, num_sms, st);
 }
 
 extern "C" {

@@ -59,16 +59,23 @@ static constexpr int kWStageKPair = 64;
 static constexpr int kWStageBytes = kTileN * kWStageK * 2;  // 16 KB
 static constexpr int kMaxKB = 10;         // H <= 640
 static constexpr int kMaxWStages = 4;
-static constexpr int kNumThreads = 640;
-static constexpr int kNumProducerWarps = 8;
-static constexpr int kNumEpilogueWarps = 8;
-// Warp ids: the SM's warp arbiter serves the highest warp id first, and the single MMA-issuing lane is the
-// serial resource of the kernel, so it gets the highest id; the TMA lanes come next, the bulk workers last.
-static constexpr int kFirstEpilogueWarp = 0;   // warps 0-7  (TMEM lane quarter = warp & 3)
-static constexpr int kFirstProducerWarp = 8;   // warps 8-15
-static constexpr int kWarpTmaW = 16;
-static constexpr int kWarpRelayA = 18;    // partner CTA of a pair only
-static constexpr int kWarpMma = 19;       // leader: MMA issue; partner: accumulator-release relay
+// Warp roles.  The SM's warp arbiter serves the highest warp id first, and the single MMA-issuing lane is the serial
+// resource of the kernel, so it gets the highest id; the TMA lanes come next, the bulk workers last.
+//   NPW = 8  (default): warps 0-7 epilogue (two column groups), 8-15 A producers, 16 TMA, 18 relay, 19 MMA  (640 threads)
+//   NPW = 16 (narrow vocabularies, V <= 128: ONE vocabulary tile per cell tile, so the A operand is built once per
+//             32..128 columns of MMA work and its producers pace the kernel -- the recipe as shipped has V = 29):
+//             warps 0-3 epilogue (one column group), 4-19 A producers, 20 TMA, 22 relay, 23 MMA            (768 threads)
+template <int NPW>
+struct Roles {
+    static constexpr int kEpilogueWarps = NPW == 16 ? 4 : 8;  // TMEM lane quarter = warp & 3
+    static constexpr int kFirstProducerWarp = kEpilogueWarps;
+    static constexpr int kWarpTmaW = kEpilogueWarps + NPW;
+    static constexpr int kWarpRelayA = kWarpTmaW + 2;  // partner CTA of a pair only
+    static constexpr int kWarpMma = kWarpTmaW + 3;     // leader: MMA issue; partner: accumulator-release relay
+    static constexpr int kThreads = (kWarpTmaW + 4) * 32;
+    static constexpr int kRowsPerThread = 32 / NPW;    // A rows per producer thread: 4 (rows rg + 32 i) or 2 (rows rg + 64 i)
+    static constexpr int kRowStride = 4 * NPW;
+};
 static constexpr float kLog2eF = 1.4426950408889634f;
 static constexpr float kLn2F = 0.6931471805599453f;
 
@@ -94,6 +101,9 @@ struct JointParams {
     int NT;                     // ceil(V / 256)
     int n_last;                 // UMMA N of the last vocabulary tile (multiple of 16)
     int num_w_stages;
+    int w_resident;             // pairs, one narrow vocabulary tile (NT == 1): all KB k-slices of W ([n_last / 2 rows x 64 h] per CTA) are loaded ONCE
+                                // and stay in the W area for the whole kernel -- no W stream, no w_full / w_empty traffic per cell tile
+    int w_stage_bytes;          // distance of consecutive W k-slices in shared memory (kWStageBytes unless w_resident)
     int dbg_skip;               // development ablations (bits): 1 epilogue only releases, 2 producers only arrive, 4 no W stream,
                                 // 8 epilogue loads but no math, 16 epilogue math but no TMEM loads, 32 MMA issue skipped
     const __nv_bfloat16* enc;   // [B,T,H]
@@ -196,25 +206,27 @@ __device__ __forceinline__ float act_t(float x, float param) {
 // A producers: J k-blocks straight from enc / dec in global memory (L1/L2 resident: every enc row of a tile is
 // read by tU threads, every dec row by tT).  The loads run two k-blocks ahead of the block being processed,
 // so their latency hides behind the arithmetic and the a_empty wait.
-template <int MODE, int ACT, bool PAIR>
+template <int MODE, int ACT, bool PAIR, int NPW>
 __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a, const __nv_bfloat16* __restrict__ enc,
                                           const __nv_bfloat16* __restrict__ dec, uint64_t* a_full, uint64_t* a_empty) {
+    using R = Roles<NPW>;
+    constexpr int NR = R::kRowsPerThread, RS = R::kRowStride;
     Rounds<PAIR> rounds(p, count_live_tiles_warp(p));
     // The partner CTA's producers arrive on a LOCAL barrier (a_full points at a_done there); a relay warp
     // forwards it to the leader.  A remote arrive has cluster-scope release semantics (MEMBAR.GPU), which in
     // MODE_GRAD would make every producer warp wait for its J-image global stores to drain.
     const int lane = threadIdx.x & 31;
-    const int ptid = threadIdx.x - kFirstProducerWarp * 32;  // 0..255
+    const int ptid = threadIdx.x - R::kFirstProducerWarp * 32;  // 0 .. 32 NPW - 1
     const int c = ptid & 7;                                  // 16-byte chunk inside the 128-byte row
-    const int rg = ptid >> 3;                                // rows rg, rg+32, rg+64, rg+96
+    const int rg = ptid >> 3;                                // rows rg + RS i, i < NR
     const int tT = 1 << p.tT_log2, tTm = tT - 1;
     const int KB = p.KB;
     uint32_t it = 0;
     const bool slope_le1 = p.act_param >= 0.f && p.act_param <= 1.f;
-    int ti[4], ui[4];
+    int ti[NR], ui[NR];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = rg + 32 * i;
+    for (int i = 0; i < NR; ++i) {
+        const int r = rg + RS * i;
         ti[i] = r & tTm;
         ui[i] = r >> p.tT_log2;
     }
@@ -231,38 +243,37 @@ __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a,
             ++it;
             continue;
         }
-        // The four rows of a thread (rg, rg + 32, rg + 64, rg + 96) share their frame index ti (32 is a multiple of every
-        // tT), so they read the SAME enc row: one enc load + four dec loads per k-block instead of eight loads.  The
-        // registers that saves pay for a second k-block of prefetch (two register sets used alternately: set A holds the even
-        // k-blocks, set B the odd ones; a set is refilled with k-block kb + 2 right after k-block kb has been consumed),
-        // which matters where the producers pace the kernel (few vocabulary tiles per cell tile: V = 29 of the recipe as
-        // shipped) and trims their LSU instructions by 3/8 everywhere.
-        bool ok[4];
-        const uint4* dp[4];
+        // The rows of a thread (rg + RS i; RS = 32 or 64 is a multiple of every tT) share their frame index ti, so they
+        // read the SAME enc row: one enc load + NR dec loads per k-block instead of 2 NR loads.  The registers that saves
+        // pay for a second k-block of prefetch (two register sets used alternately: set A holds the even k-blocks, set B
+        // the odd ones; a set is refilled with k-block kb + 2 right after k-block kb has been consumed), which matters
+        // where the producers pace the kernel (few vocabulary tiles per cell tile) and trims their LSU instructions.
+        bool ok[NR];
+        const uint4* dp[NR];
         const int t_row = min(tc.t0 + ti[0], p.T - 1);
         const uint4* ep = reinterpret_cast<const uint4*>(enc + ((size_t)tc.b * p.T + t_row) * p.H) + c;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NR; ++i) {
             ok[i] = tc.t0 + ti[i] < tc.Tb && tc.u0 + ui[i] < tc.Ub;
             // rows outside the utterance are masked below; clamp them so that the loads stay inside the tensors
             const int u = min(tc.u0 + ui[i], p.U - 1);
             dp[i] = reinterpret_cast<const uint4*>(dec + ((size_t)tc.b * p.U + u) * p.H) + c;
         }
-        uint4 evA, dvA[4], evB = make_uint4(0, 0, 0, 0), dvB[4];
+        uint4 evA, dvA[NR], evB = make_uint4(0, 0, 0, 0), dvB[NR];
         evA = __ldg(ep);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { dvA[i] = __ldg(dp[i]); dvB[i] = make_uint4(0, 0, 0, 0); }
+        for (int i = 0; i < NR; ++i) { dvA[i] = __ldg(dp[i]); dvB[i] = make_uint4(0, 0, 0, 0); }
         if (KB > 1) {  // next k-block: 64 h further = 8 chunks of 16 bytes
             evB = __ldg(ep + 8);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dvB[i] = __ldg(dp[i] + 8);
+            for (int i = 0; i < NR; ++i) dvB[i] = __ldg(dp[i] + 8);
         }
-        auto produce_block = [&](const int kb, uint4& ev, uint4 (&dv)[4]) {
+        auto produce_block = [&](const int kb, uint4& ev, uint4 (&dv)[NR]) {
             mbar_wait(&a_empty[kb], (it & 1) ^ 1, 0x500 | kb);
             uint8_t* blk = smem_a + kb * kABlockBytes;
             const uint32_t* e = reinterpret_cast<const uint32_t*>(&ev);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {  // one row at a time: four live output registers instead of sixteen
+            for (int i = 0; i < NR; ++i) {  // one row at a time: four live output registers instead of sixteen
                 const uint32_t* d = reinterpret_cast<const uint32_t*>(&dv[i]);
                 uint4 o;
                 uint32_t* op = reinterpret_cast<uint32_t*>(&o);
@@ -278,7 +289,7 @@ __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a,
                     }
                     op[w] = ok[i] ? pack_bf16x2(a.x, a.y) : 0u;
                 }
-                const uint32_t off = sw128_offset((uint32_t)(rg + 32 * i), (uint32_t)c);
+                const uint32_t off = sw128_offset((uint32_t)(rg + RS * i), (uint32_t)c);
                 *reinterpret_cast<uint4*>(blk + off) = o;
                 if (ModeTraits<MODE>::grad) {
                     uint8_t* img = reinterpret_cast<uint8_t*>(p.J_img) + ((size_t)(tile - p.tile_begin) * KB + kb) * kABlockBytes;
@@ -288,7 +299,7 @@ __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a,
             if (kb + 2 < KB) {  // refill this register set with the k-block after next
                 ev = __ldg(ep + (kb + 2) * 8);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dv[i] = __ldg(dp[i] + (kb + 2) * 8);
+                for (int i = 0; i < NR; ++i) dv[i] = __ldg(dp[i] + (kb + 2) * 8);
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -303,9 +314,14 @@ __device__ __forceinline__ void produce_a(const JointParams& p, uint8_t* smem_a,
     }
 }
 
-template <int MODE, bool PAIR>
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <int MODE, bool PAIR, int NPW>
+__global__ void __launch_bounds__(Roles<NPW>::kThreads, 1)
 joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams p) {
+    using R = Roles<NPW>;
+    constexpr int kWarpTmaW = R::kWarpTmaW, kWarpRelayA = R::kWarpRelayA, kWarpMma = R::kWarpMma;
+    constexpr int kFirstProducerWarp = R::kFirstProducerWarp, kNumProducerWarps = NPW, kNumEpilogueWarps = R::kEpilogueWarps;
+    constexpr bool kTwoGroups = kNumEpilogueWarps == 8;  // two column groups of four epilogue warps, or one (NPW = 16: V <= 128)
+    static_assert(!(NPW == 16) || PAIR, "the 16-producer form exists for CTA pairs only");
     extern __shared__ __align__(1024) uint8_t smem[];
     griddep_wait();  // programmatic dependent launch: nothing below may read global memory before the predecessor is done
     const SmemLayout L = smem_layout(p.KB, p.num_w_stages);
@@ -355,7 +371,18 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
         // ===================== W producer (TMA) =====================
         // PAIR: the leader fills BOTH halves of a stage (its own and, by multicast to CTA 1, its partner's),
         // so the refill latency is commit -> leader wake-up -> TMA, with no detour through the partner.
-        if (leader && !(p.dbg_skip & 4)) {  // whole warp, converged; one lane is elected inside each issuing instruction
+        if (PAIR && p.w_resident) {
+            // one narrow vocabulary tile: every k-slice of W (both CTAs' halves, by multicast) once, on ONE barrier
+            if (leader && rounds.count_my_rounds(n_live) > 0) {
+                const uint32_t bytes = (uint32_t)p.w_stage_bytes;
+                mbar_arrive_expect_tx_e(&w_full[0], 2u * (uint32_t)KB * bytes);
+                for (int kb = 0; kb < KB; ++kb) {
+                    uint8_t* dst = smem_w + (uint32_t)kb * bytes;
+                    tma_load_2d_2cta_mcast_e(dst, &tmap_w, &w_full[0], 1, kb * kWStageKPair, 0);
+                    tma_load_2d_2cta_mcast_e(dst, &tmap_w, &w_full[0], 2, kb * kWStageKPair, p.n_last >> 1);
+                }
+            }
+        } else if (leader && !(p.dbg_skip & 4)) {  // whole warp, converged; one lane is elected inside each issuing instruction
             uint32_t stage = 0, phase = 0;
             const int my_rounds = rounds.count_my_rounds(n_live);
             for (int round = 0; round < my_rounds; ++round) {
@@ -406,6 +433,11 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
             long long t_acc = 0, t_a = 0, t_w = 0, tm = 0, t_commit[3] = {0, 0, 0}, l_sum = 0, l_cnt = 0;
             const long long t_begin = clock64();
             const int my_rounds = rounds.count_my_rounds(n_live);
+            const bool w_res = PAIR && p.w_resident;
+            if (w_res && my_rounds > 0) {  // the resident W slices have landed (in both CTAs: one barrier collects all bytes)
+                mbar_wait(&w_full[0], 0, 0x400);
+                tcgen05_fence_after();
+            }
             for (int round = 0; round < my_rounds; ++round) {
                 for (int nt = 0; nt < NT; ++nt, ++acc_it) {
                     const uint32_t buf = acc_it & 1, acc_phase = (acc_it >> 1) & 1;
@@ -417,7 +449,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                     const uint32_t idesc = nt == NT - 1 ? idesc_last : idesc_full;
                     const bool first_nt = nt == 0, last_nt = nt == NT - 1;
                     uint32_t a_lo = a_lo0;
-                    if (PAIR && NS == 4 && !(KB & 1) && !(p.dbg_skip & 256)) {
+                    if (PAIR && NS == 4 && !(KB & 1) && !(p.dbg_skip & 256) && !w_res) {
                         // Two k-blocks (8 MMAs) per wait / commit group: measured 5 % faster than one group per k-block (the
                         // per-stage wait -> 4 MMAs -> commit structure, not the W bytes, is what the W stream costs; bit 256 of
                         // TSASR_DEBUG_SKIP selects the per-stage loop for A/B runs)
@@ -447,7 +479,11 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                             if (p.prof) t_a += clock64() - tm;
                             tcgen05_fence_after();
                         }
-                        if (PAIR) {
+                        if (PAIR && w_res) {  // W slice kb sits at its fixed place: nothing to wait for, nothing to release
+                            umma_bf16_2cta_x4_e(d_tmem, ((uint64_t)a_hi << 32) | a_lo,
+                                                ((uint64_t)w_hi << 32) | (w_lo0 + (uint32_t)kb * ((uint32_t)p.w_stage_bytes >> 4)), idesc, kb != 0);
+                            umma_commit_2cta_e(&a_empty[kb], 3);  // NT == 1: every vocabulary tile is the last one
+                        } else if (PAIR) {
                             if (p.prof) tm = clock64();
                             if (!(p.dbg_skip & 4)) mbar_wait(&w_full[stage], phase, 0x400 | stage);
                             if (p.prof) t_w += clock64() - tm;
@@ -520,17 +556,17 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
         // ===================== A producers: J = bf16(act(enc + dec)) =====================
         uint64_t* a_arrive = (PAIR && !leader) ? a_done : a_full;
         switch (p.act_kind) {
-            case ACT_LEAKY_RELU: produce_a<MODE, ACT_LEAKY_RELU, PAIR>(p, smem_a, p.enc, p.dec, a_arrive, a_empty); break;
-            case ACT_RELU: produce_a<MODE, ACT_RELU, PAIR>(p, smem_a, p.enc, p.dec, a_arrive, a_empty); break;
-            case ACT_TANH: produce_a<MODE, ACT_TANH, PAIR>(p, smem_a, p.enc, p.dec, a_arrive, a_empty); break;
-            default: produce_a<MODE, ACT_IDENTITY, PAIR>(p, smem_a, p.enc, p.dec, a_arrive, a_empty); break;
+            case ACT_LEAKY_RELU: produce_a<MODE, ACT_LEAKY_RELU, PAIR, NPW>(p, smem_a, p.enc, p.dec, a_arrive, a_empty); break;
+            case ACT_RELU: produce_a<MODE, ACT_RELU, PAIR, NPW>(p, smem_a, p.enc, p.dec, a_arrive, a_empty); break;
+            case ACT_TANH: produce_a<MODE, ACT_TANH, PAIR, NPW>(p, smem_a, p.enc, p.dec, a_arrive, a_empty); break;
+            default: produce_a<MODE, ACT_IDENTITY, PAIR, NPW>(p, smem_a, p.enc, p.dec, a_arrive, a_empty); break;
         }
-    } else if (warp_idx < kFirstEpilogueWarp + kNumEpilogueWarps) {
+    } else if (warp_idx < kNumEpilogueWarps) {
         // ===================== epilogue =====================
-        const int grp = (warp_idx - kFirstEpilogueWarp) >> 2;  // column half of every vocabulary tile owned by this group
+        const int grp = kTwoGroups ? warp_idx >> 2 : 0;        // column half of every vocabulary tile owned by this group
         const int q = warp_idx & 3;                            // TMEM lane quarter owned by this warp
         const int row = q * 32 + lane;                         // tile row == TMEM lane
-        const int gtid = (threadIdx.x - kFirstEpilogueWarp * 32) & 127;  // 0..127 inside the group
+        const int gtid = threadIdx.x & 127;                    // 0..127 inside the group
         const int tTm = (1 << p.tT_log2) - 1;
         const int n_lab = max(1, 32 >> p.tT_log2);  // distinct label positions inside one warp
         const uint32_t tmem_row0 = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -557,7 +593,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_release[buf]);
                 }
-                if (MODE == MODE_FWD) {  // the merge of a cell tile passes four barriers
+                if (MODE == MODE_FWD && kTwoGroups) {  // the merge of a cell tile passes four barriers
 #pragma unroll
                     for (int i = 0; i < 4; ++i) asm volatile("bar.sync 3, 256;" ::: "memory");
                 }
@@ -817,16 +853,18 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const JointParams 
                 // merge the two groups' running (max, sum) and picked logits; group 0 writes the lattice.  The exchange
                 // buffer is one float2 per row and is used twice ((max, sum), then the picked logits): the shared memory
                 // saved buys the fourth W stage at H = 640.  Barriers: buffer free / (max, sum) written / read / picks written.
-                asm volatile("bar.sync 3, 256;" ::: "memory");
-                if (grp == 1) xchg[row] = make_float2(run_m, run_s);
-                asm volatile("bar.sync 3, 256;" ::: "memory");
-                float2 o_ms = make_float2(-INFINITY, 0.f);
-                if (grp == 0) o_ms = xchg[row];
-                asm volatile("bar.sync 3, 256;" ::: "memory");
-                if (grp == 1) xchg[row] = make_float2(y_blank, y_label);
-                asm volatile("bar.sync 3, 256;" ::: "memory");
+                float2 o_ms = make_float2(-INFINITY, 0.f), o_y = make_float2(-INFINITY, -INFINITY);
+                if (kTwoGroups) {
+                    asm volatile("bar.sync 3, 256;" ::: "memory");
+                    if (grp == 1) xchg[row] = make_float2(run_m, run_s);
+                    asm volatile("bar.sync 3, 256;" ::: "memory");
+                    if (grp == 0) o_ms = xchg[row];
+                    asm volatile("bar.sync 3, 256;" ::: "memory");
+                    if (grp == 1) xchg[row] = make_float2(y_blank, y_label);
+                    asm volatile("bar.sync 3, 256;" ::: "memory");
+                    if (grp == 0 && valid) o_y = xchg[row];
+                }
                 if (grp == 0 && valid) {
-                    const float2 o_y = xchg[row];
                     const float mn = fmaxf(run_m, o_ms.x);
                     const float s = run_s * ex2_approx(run_m - mn) + o_ms.y * ex2_approx(o_ms.x - mn);
                     const float lz2 = mn + lg2_approx(s);
