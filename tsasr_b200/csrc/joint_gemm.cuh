@@ -6,7 +6,7 @@
 // Linear (SB/nnet/linear.py:74) and the log-softmax that follows (SB/nnet/losses.py:72-79,84) without
 // ever writing J ([B,T,U,H]) or the logits ([B,T,U,V]) to HBM.
 //
-// One persistent CTA per SM, 20 warps (640 threads):
+// One persistent CTA per SM, 20 warps (640 threads; Roles<8>, the default form):
 //   warp 16      TMA producer: streams W k-slices through a 4-stage ring (3 when the shared memory is short); the MMA lane
 //                consumes them two at a time (8 MMAs per wait / commit group)
 //   warp 19      allocates TMEM, then ONE lane issues tcgen05.mma (N<=256, K=16, bf16 -> fp32); highest warp id
@@ -36,6 +36,12 @@
 // loads only HALF of every W stage and owns the accumulator rows of its own tile.  That halves the
 // L2->SM traffic of the W stream (the measured bottleneck of the single-CTA kernel) and doubles the
 // tensor work per issued instruction.
+//
+// NPW = 16 is the form for NARROW vocabularies (one vocabulary tile of at most 128 columns per cell tile: the recipe as
+// shipped has 29 characters): warps 0-3 epilogue (one column group), warps 4-19 A producers, 20 TMA, 22 relay, 23 MMA
+// (Roles<16>, 768 threads); and when the CTA's share of W fits the W area (JointParams::w_resident) every k-slice of W is
+// loaded ONCE and stays for the whole kernel.  With one small MMA group per k-block the W ring's refill latency and the
+// A producers pace the kernel, not the tensor pipe (profiles/r2_narrow_vocabulary.txt: forward 796 -> 508 us at V = 29).
 //
 // A cell tile is tT consecutive frames x tU consecutive label positions of one utterance
 // (tT * tU = 128, tT in {8,16,32}, row r = ui * tT + ti); tiles completely outside the utterance's
